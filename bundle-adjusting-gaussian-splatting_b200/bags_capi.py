@@ -1,0 +1,82 @@
+"""ctypes binding of libbags_b200.so -- the C ABI declared in include/bags_b200.h.
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import (CFUNCTYPE, POINTER, c_char_p, c_float, c_int, c_size_t, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbags_b200.so")
+
+ALLOC_FN = CFUNCTYPE(c_void_p, c_size_t, c_void_p)
+
+_lib = None
+
+# every symbol include/bags_b200.h declares: (restype, argtypes)
+_P = c_void_p
+SIGNATURES = {
+    "bags_last_error": (c_char_p, []),
+    "bags_version": (c_int, []),
+    "bags_geom_bytes": (c_size_t, [c_int]),
+    "bags_image_bytes": (c_size_t, [c_int, c_int]),
+    "bags_binning_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "bags_backward_scratch_bytes": (c_size_t, [c_int]),
+    "bags_rasterize_forward": (c_int, [ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P,      # allocators
+                                       c_int, c_int, c_int,                          # P, D, M
+                                       _P, c_int, c_int,                             # background, width, height
+                                       _P, _P, _P, _P,                               # means3D, shs, colors, opacities
+                                       _P, c_float, _P, _P,                          # scales, mod, rotations, cov3D
+                                       _P, _P, _P, _P, _P,                           # view, proj, intrinsic, campos, shift
+                                       c_float, c_float, c_int,                      # tanfovx, tanfovy, prefiltered
+                                       _P, _P, _P, _P, _P, _P,                       # color, depth, alpha, radii, m2Dx, m2Dy
+                                       c_int, _P]),                                  # debug, stream
+    "bags_rasterize_backward": (c_int, [c_int, c_int, c_int, c_int,                  # P, D, M, R
+                                        _P, c_int, c_int,                            # background, width, height
+                                        _P, _P, _P, _P,                              # means3D, shs, colors, alphas
+                                        _P, c_float, _P, _P,                         # scales, mod, rotations, cov3D
+                                        _P, _P, _P, _P,                              # view, proj, intrinsic, campos
+                                        c_float, c_float,                            # tanfovx, tanfovy
+                                        _P, _P, _P, _P,                              # radii, geom, binning, image
+                                        _P, _P, _P,                                  # dL_dpix, dL_ddepth, dL_dalpha
+                                        _P,                                          # scratch
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,      # dense outputs
+                                        _P, _P, _P, _P,                              # proj, view, campos, shift
+                                        c_int, _P]),                                 # debug, stream
+    "bags_mark_visible": (c_int, [c_int, _P, _P, _P, _P, _P]),
+    "bags_compute_relocation": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "bags_knn_scratch_bytes": (c_size_t, [c_int]),
+    "bags_knn_mean_dist2": (c_int, [c_int, _P, _P, _P, _P]),
+    "bags_unpack_state": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P,
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bags_sort_scratch_bytes": (c_size_t, [c_int]),
+    "bags_sort_pairs_u32": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
+}
+
+
+class BagsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the library on first use.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BagsError(
+                f"{LIB_PATH} not found: build it with `python {os.path.join(_HERE, 'build.py')}` "
+                "(there is no CPU or PyTorch fallback for the rasterizer)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc < 0:
+        msg = lib().bags_last_error()
+        raise BagsError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+    return rc

@@ -1,0 +1,365 @@
+// C ABI entry points (include/bags_b200.h): state layouts, host orchestration of the forward / backward pipelines,
+// and the test-only state unpacker.  Host logic follows CudaRasterizer::Rasterizer::forward / backward
+// (3dgs-pose/cuda_rasterizer/rasterizer_impl.cu:198-349,353-475) and RasterizeGaussians[Backward]CUDA
+// (3dgs-pose/rasterize_points.cu:36-276) of the reference; see DESIGN.md for what is fused or reordered.
+#include "../../include/bags_b200.h"
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace bags {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- state layouts -----------------------------------------------------------------------------------------------
+static inline size_t emit_tiles(int P) { return (size_t)(P + EMIT_THREADS - 1) / EMIT_THREADS + 1; }
+
+size_t GeomState::bytes(int P) {
+    size_t n = (size_t)P;
+    return align_up(3 * n * sizeof(float4)) + align_up(n * sizeof(ushort4)) + 4 * align_up(n * sizeof(u32)) +
+           align_up(4 * sizeof(unsigned long long)) + align_up(emit_tiles(P) * sizeof(u32)) + SortScratch::bytes(P) +
+           256;
+}
+
+GeomState GeomState::from(char* p, int P) {
+    GeomState g;
+    p = (char*)align_up((size_t)p);
+    size_t n = (size_t)P;
+    carve(p, g.rec, 3 * n);
+    carve(p, g.rect, n);
+    carve(p, g.key_a, n);
+    carve(p, g.key_b, n);
+    carve(p, g.idx_a, n);
+    carve(p, g.idx_b, n);
+    carve(p, g.counters, 4);
+    carve(p, g.emit_status, emit_tiles(P));
+    g.sort = SortScratch::from(p, P);
+    return g;
+}
+
+size_t BinningState::bytes(int R) {
+    size_t n = (size_t)(R > 0 ? R : 1);
+    return 4 * align_up(n * sizeof(u32)) + SortScratch::bytes(R) + 256;
+}
+
+BinningState BinningState::from(char* p, int R, int npass) {
+    BinningState b;
+    p = (char*)align_up((size_t)p);
+    size_t n = (size_t)(R > 0 ? R : 1);
+    // id buffers first: the one holding point_list is what backward keeps reading
+    carve(p, b.id_buf[0], n);
+    carve(p, b.id_buf[1], n);
+    carve(p, b.tile_buf[0], n);
+    carve(p, b.tile_buf[1], n);
+    b.sort = SortScratch::from(p, R);
+    b.point_list = b.id_buf[npass & 1];
+    b.tile_sorted = b.tile_buf[npass & 1];
+    return b;
+}
+
+size_t ImageState::bytes(int width, int height) {
+    size_t N = (size_t)width * height;
+    size_t T = (size_t)tiles_x(width) * tiles_y(height);
+    return 2 * align_up(N * 4) + align_up(T * sizeof(uint2)) + 256;
+}
+
+ImageState ImageState::from(char* p, int width, int height) {
+    ImageState s;
+    p = (char*)align_up((size_t)p);
+    size_t N = (size_t)width * height;
+    size_t T = (size_t)tiles_x(width) * tiles_y(height);
+    carve(p, s.final_T, N);
+    carve(p, s.n_contrib, N);
+    carve(p, s.ranges, T);
+    return s;
+}
+
+// ---- per-device host resources: a pinned word for num_rendered and an event --------------------------------------
+struct DeviceCtx {
+    unsigned long long* pinned = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+static DeviceCtx g_ctx[64];
+
+static int get_ctx(DeviceCtx** out) {
+    int dev = 0;
+    BAGS_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("device index %d out of range", dev);
+        return BAGS_E_INVALID;
+    }
+    DeviceCtx& c = g_ctx[dev];
+    if (!c.pinned) {
+        BAGS_CUDA_OK(cudaMallocHost((void**)&c.pinned, 64));
+        BAGS_CUDA_OK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+    }
+    *out = &c;
+    return 0;
+}
+
+// ---- unpack kernels (test-only) ----------------------------------------------------------------------------------
+__global__ void unpack_geom_kernel(int P, const float4* __restrict__ rec, const ushort4* __restrict__ rect,
+                                   u32* tiles_touched, u32* depth_bits, float* xy, float* conic_opacity,
+                                   float* rgb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    ushort4 r = rect[i];
+    u32 tt = (u32)r.z * (u32)r.w;
+    if (tiles_touched) tiles_touched[i] = tt;
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+    if (tt) {
+        q0 = rec[3 * (size_t)i];
+        q1 = rec[3 * (size_t)i + 1];
+        q2 = rec[3 * (size_t)i + 2];
+    }
+    if (depth_bits) depth_bits[i] = __float_as_uint(q0.z);
+    if (xy) { xy[2 * i] = q0.x; xy[2 * i + 1] = q0.y; }
+    if (conic_opacity) {
+        conic_opacity[4 * i] = q1.x; conic_opacity[4 * i + 1] = q1.y;
+        conic_opacity[4 * i + 2] = q1.z; conic_opacity[4 * i + 3] = q1.w;
+    }
+    if (rgb) { rgb[3 * i] = q2.x; rgb[3 * i + 1] = q2.y; rgb[3 * i + 2] = q2.z; }
+}
+
+__global__ void unpack_binning_kernel(int R, const u32* __restrict__ point_list, const u32* __restrict__ tile_sorted,
+                                      const float4* __restrict__ rec, u32* out_list, u64* out_keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    u32 id = point_list[i];
+    if (out_list) out_list[i] = id;
+    if (out_keys) out_keys[i] = ((u64)tile_sorted[i] << 32) | (u64)__float_as_uint(rec[3 * (size_t)id].z);
+}
+
+int launch_unpack(int P, int R, int W, int H, const GeomState& g, const BinningState& b, const ImageState& img,
+                  u32* tiles_touched, u32* depth_bits, float* xy, float* conic_opacity, float* rgb, u32* point_list,
+                  u64* point_list_keys, u32* ranges, u32* n_contrib, float* final_T, cudaStream_t st) {
+    if (P > 0 && (tiles_touched || depth_bits || xy || conic_opacity || rgb)) {
+        unpack_geom_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, g.rec, g.rect, tiles_touched, depth_bits, xy,
+                                                            conic_opacity, rgb);
+        BAGS_LAUNCH_OK("unpack_geom_kernel");
+    }
+    if (R > 0 && (point_list || point_list_keys)) {
+        unpack_binning_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, b.point_list, b.tile_sorted, g.rec, point_list,
+                                                               point_list_keys);
+        BAGS_LAUNCH_OK("unpack_binning_kernel");
+    }
+    size_t N = (size_t)W * H, T = (size_t)tiles_x(W) * tiles_y(H);
+    if (ranges) BAGS_CUDA_OK(cudaMemcpyAsync(ranges, img.ranges, T * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
+    if (n_contrib) BAGS_CUDA_OK(cudaMemcpyAsync(n_contrib, img.n_contrib, N * 4, cudaMemcpyDeviceToDevice, st));
+    if (final_T) BAGS_CUDA_OK(cudaMemcpyAsync(final_T, img.final_T, N * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace bags
+
+using namespace bags;
+
+extern "C" const char* bags_last_error(void) { return g_err; }
+extern "C" int bags_version(void) { return 100; }
+
+extern "C" size_t bags_geom_bytes(int P) { return GeomState::bytes(P < 0 ? 0 : P); }
+extern "C" size_t bags_image_bytes(int width, int height) { return ImageState::bytes(width, height); }
+extern "C" size_t bags_binning_bytes(int P, int num_rendered, int width, int height) {
+    (void)P; (void)width; (void)height;
+    return BinningState::bytes(num_rendered);
+}
+extern "C" size_t bags_backward_scratch_bytes(int P) {
+    return align_up((size_t)(P < 0 ? 0 : P) * GACC_STRIDE * sizeof(float)) + 256 + 256;
+}
+
+#define BAGS_REQUIRE(cond, msg)                      \
+    do {                                             \
+        if (!(cond)) {                               \
+            set_error("%s: %s", __func__, msg);      \
+            return BAGS_E_INVALID;                   \
+        }                                            \
+    } while (0)
+
+extern "C" int bags_rasterize_forward(
+    bags_alloc_fn geom_alloc, void* geom_user, bags_alloc_fn binning_alloc, void* binning_user,
+    bags_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+    float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+    const float* projmatrix, const float* intrinsic, const float* cam_pos, const float* shift_factors, float tan_fovx,
+    float tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha, int* radii, float* mean2Dx,
+    float* mean2Dy, int debug, void* stream) {
+    (void)intrinsic;  // passed through by the reference too, never read by live code (forward.cu:352)
+    cudaStream_t st = (cudaStream_t)stream;
+    BAGS_REQUIRE(P >= 0 && width > 0 && height > 0, "negative P or empty image");
+    BAGS_REQUIRE(out_color && out_depth && out_alpha, "null output image");
+    BAGS_REQUIRE(geom_alloc && binning_alloc && image_alloc, "null allocation callback");
+    const size_t N = (size_t)width * height;
+    if (P == 0) {
+        // reference: kernels skipped, zero-initialised outputs returned (rasterize_points.cu:66-83)
+        BAGS_CUDA_OK(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(out_depth, 0, N * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(out_alpha, 0, N * sizeof(float), st));
+        return 0;
+    }
+    BAGS_REQUIRE(background && means3D && opacities && viewmatrix && projmatrix && cam_pos && shift_factors,
+                 "null required input");
+    BAGS_REQUIRE(radii && mean2Dx && mean2Dy, "null per-Gaussian output");
+    BAGS_REQUIRE((shs != nullptr) != (colors_precomp != nullptr), "provide exactly one of shs / colors_precomp");
+    BAGS_REQUIRE((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr),
+                 "provide exactly one of scales+rotations / cov3D_precomp");
+    BAGS_REQUIRE(shs == nullptr || (M >= (D + 1) * (D + 1) && D >= 0 && D <= 3), "SH degree / coefficient count");
+    BAGS_REQUIRE(tiles_x(width) <= 65535 && tiles_y(height) <= 65535, "image too large for 16-bit tile coordinates");
+
+    DeviceCtx* ctx;
+    int rc = get_ctx(&ctx);
+    if (rc) return rc;
+
+    char* geom_ptr = geom_alloc(GeomState::bytes(P), geom_user);
+    char* img_ptr = image_alloc(ImageState::bytes(width, height), image_user);
+    if (!geom_ptr || !img_ptr) {
+        set_error("allocation callback returned NULL");
+        return BAGS_E_ALLOC;
+    }
+    GeomState g = GeomState::from(geom_ptr, P);
+    ImageState img = ImageState::from(img_ptr, width, height);
+
+    FwdArgs a;
+    a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
+    a.background = background; a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp;
+    a.opacities = opacities; a.scales = scales; a.scale_modifier = scale_modifier; a.rotations = rotations;
+    a.cov3D_precomp = cov3D_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+    a.shift_factors = shift_factors; a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+    a.focal_y = height / (2.0f * tan_fovy);
+    a.focal_x = width / (2.0f * tan_fovx);
+    a.prefiltered = prefiltered;
+
+    // counters + emit chained-scan words are contiguous: one memset
+    BAGS_CUDA_OK(cudaMemsetAsync(g.counters, 0, (char*)g.sort.ghist - (char*)g.counters, st));
+    rc = launch_preprocess_fwd(a, g, radii, mean2Dx, mean2Dy, st);
+    if (rc) return rc;
+
+    // num_rendered travels to the host while the depth sort runs
+    BAGS_CUDA_OK(cudaMemcpyAsync(ctx->pinned, g.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    BAGS_CUDA_OK(cudaEventRecord(ctx->ev, st));
+
+    u32 *sorted_keys, *sorted_idx;
+    rc = launch_sort_pairs(P, g.key_a, g.idx_a, g.key_b, g.idx_b, 0, 32, g.sort, true, st, &sorted_keys, &sorted_idx);
+    if (rc) return rc;
+
+    BAGS_CUDA_OK(cudaEventSynchronize(ctx->ev));
+    const unsigned long long R64 = *ctx->pinned;
+    if (R64 >= (1ull << 30)) {
+        set_error("num_rendered = %llu does not fit the 30-bit look-back words", R64);
+        return BAGS_E_OVERFLOW;
+    }
+    const int R = (int)R64;
+    const int ntiles = tiles_x(width) * tiles_y(height);
+    const int npass = tile_sort_passes(ntiles);
+
+    char* bin_ptr = binning_alloc(BinningState::bytes(R), binning_user);
+    if (!bin_ptr) {
+        set_error("binning allocation callback returned NULL");
+        return BAGS_E_ALLOC;
+    }
+    BinningState b = BinningState::from(bin_ptr, R, npass);
+
+    if (R > 0) {
+        rc = launch_emit(P, g, sorted_idx, b, tiles_x(width), st);
+        if (rc) return rc;
+        u32 *fk, *fv;
+        rc = launch_sort_pairs(R, b.tile_buf[0], b.id_buf[0], b.tile_buf[1], b.id_buf[1], 0, tile_sort_bits(ntiles),
+                               b.sort, false, st, &fk, &fv);
+        if (rc) return rc;
+        if (fv != b.point_list || fk != b.tile_sorted) {
+            set_error("internal: tile sort ping-pong parity mismatch");
+            return BAGS_E_INVALID;
+        }
+    }
+    rc = launch_ranges(R, ntiles, b.tile_sorted, img.ranges, st);
+    if (rc) return rc;
+    rc = launch_blend_fwd(width, height, g, b, img, background, out_color, out_depth, out_alpha, st);
+    if (rc) return rc;
+    if (debug) BAGS_CUDA_OK(cudaStreamSynchronize(st));
+    return R;
+}
+
+extern "C" int bags_rasterize_backward(
+    int P, int D, int M, int R, const float* background, int width, int height, const float* means3D,
+    const float* shs, const float* colors_precomp, const float* alphas, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+    const float* intrinsic, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer, const float* dL_dpix,
+    const float* dL_dpix_depth, const float* dL_dalpha, char* scratch, float* dL_dmean2D, float* dL_dmean2D_densify,
+    float* covariance, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+    float* dL_dscale, float* dL_drot, float* dL_dprojmatrix, float* dL_dviewmatrix, float* dL_dcampos,
+    float* dL_dshift, int debug, void* stream) {
+    (void)intrinsic; (void)alphas; (void)colors_precomp;
+    cudaStream_t st = (cudaStream_t)stream;
+    BAGS_REQUIRE(P >= 0 && R >= 0 && width > 0 && height > 0, "negative size");
+    BAGS_REQUIRE(scratch && dL_dprojmatrix && dL_dviewmatrix && dL_dcampos && dL_dshift, "null pose output/scratch");
+
+    char* sp = (char*)align_up((size_t)scratch);
+    float* gacc = (float*)sp;
+    float* pose_acc = (float*)(sp + align_up((size_t)P * GACC_STRIDE * sizeof(float)));
+    BAGS_CUDA_OK(cudaMemsetAsync(sp, 0, align_up((size_t)P * GACC_STRIDE * sizeof(float)) + 256, st));
+
+    BwdOut o;
+    o.dL_dmean2D = dL_dmean2D; o.dL_dmean2D_densify = dL_dmean2D_densify; o.covariance = covariance;
+    o.dL_dopacity = dL_dopacity; o.dL_dcolor = dL_dcolor; o.dL_dmean3D = dL_dmean3D; o.dL_dcov3D = dL_dcov3D;
+    o.dL_dsh = dL_dsh; o.dL_dscale = dL_dscale; o.dL_drot = dL_drot; o.dL_dprojmatrix = dL_dprojmatrix;
+    o.dL_dviewmatrix = dL_dviewmatrix; o.dL_dcampos = dL_dcampos; o.dL_dshift = dL_dshift;
+
+    BwdArgs a;
+    a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
+    a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales;
+    a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+    a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.campos = campos; a.tan_fovx = tan_fovx;
+    a.tan_fovy = tan_fovy;
+    a.focal_y = height / (2.0f * tan_fovy);
+    a.focal_x = width / (2.0f * tan_fovx);
+    a.radii = radii;
+
+    GeomState g;
+    memset(&g, 0, sizeof(g));
+    if (P > 0) {
+        BAGS_REQUIRE(background && means3D && viewmatrix && projmatrix && campos && radii, "null required input");
+        BAGS_REQUIRE(geom_buffer && binning_buffer && image_buffer, "null state buffer");
+        BAGS_REQUIRE(dL_dpix && dL_dpix_depth && dL_dalpha, "null upstream gradient");
+        BAGS_REQUIRE(dL_dmean2D && dL_dmean2D_densify && covariance && dL_dopacity && dL_dcolor && dL_dmean3D &&
+                         dL_dcov3D && dL_dscale && dL_drot,
+                     "null dense output");
+        BAGS_REQUIRE(shs == nullptr || dL_dsh != nullptr, "null dL_dsh with SH input");
+        BAGS_REQUIRE((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr),
+                     "provide exactly one of scales+rotations / cov3D_precomp");
+        g = GeomState::from(const_cast<char*>(geom_buffer), P);
+        const int ntiles = tiles_x(width) * tiles_y(height);
+        BinningState b = BinningState::from(const_cast<char*>(binning_buffer), R, tile_sort_passes(ntiles));
+        ImageState img = ImageState::from(const_cast<char*>(image_buffer), width, height);
+        if (R > 0) {
+            int rc = launch_blend_bwd(width, height, g, b, img, background, dL_dpix, dL_dpix_depth, dL_dalpha, gacc,
+                                      st);
+            if (rc) return rc;
+        }
+    }
+    int rc = launch_preprocess_bwd(a, g, gacc, pose_acc, o, st);
+    if (rc) return rc;
+    if (debug) BAGS_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int bags_unpack_state(int P, int R, int width, int height, const char* geom_buffer,
+                                 const char* binning_buffer, const char* image_buffer, uint32_t* tiles_touched,
+                                 uint32_t* depth_bits, float* xy, float* conic_opacity, float* rgb,
+                                 uint32_t* point_list, uint64_t* point_list_keys, uint32_t* ranges,
+                                 uint32_t* n_contrib, float* final_T, void* stream) {
+    BAGS_REQUIRE(P > 0 && R >= 0 && geom_buffer && binning_buffer && image_buffer, "invalid argument");
+    GeomState g = GeomState::from(const_cast<char*>(geom_buffer), P);
+    const int ntiles = tiles_x(width) * tiles_y(height);
+    BinningState b = BinningState::from(const_cast<char*>(binning_buffer), R, tile_sort_passes(ntiles));
+    ImageState img = ImageState::from(const_cast<char*>(image_buffer), width, height);
+    return launch_unpack(P, R, width, height, g, b, img, tiles_touched, depth_bits, xy, conic_opacity, rgb,
+                         point_list, (u64*)point_list_keys, ranges, n_contrib, final_T, (cudaStream_t)stream);
+}

@@ -1,0 +1,208 @@
+// Internal shared definitions for the sm_100a rasterizer kernels (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+
+namespace bags {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// Tile geometry is part of the parity contract (config.h:16-17 of the reference: 16x16 pixel tiles).
+constexpr int TILE_X = 16;
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+
+// ---- error plumbing --------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define BAGS_CUDA_OK(expr)                                                                       \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            bags::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                 \
+                            cudaGetErrorString(_e));                                             \
+            return BAGS_E_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+#define BAGS_LAUNCH_OK(name)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess) {                                                                 \
+            bags::set_error("launch of %s failed at %s:%d: %s", name, __FILE__, __LINE__,        \
+                            cudaGetErrorString(_e));                                             \
+            return BAGS_E_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+// ---- opaque state layouts --------------------------------------------------------------------------------------
+// Every sub-array starts on a 256-byte boundary relative to a 256-byte aligned base.
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+template <typename T>
+inline void carve(char*& p, T*& out, size_t count) {
+    out = reinterpret_cast<T*>(p);
+    p += align_up(count * sizeof(T));
+}
+
+// Radix-sort bookkeeping shared by the depth sort (P items) and the tile sort (R items).
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 8192 keys per CTA
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_MAX_PASSES = 4;
+
+struct SortScratch {
+    u32* ghist;        // [SORT_MAX_PASSES][RADIX] global digit histograms
+    u32* tile_counter; // [SORT_MAX_PASSES] dynamic tile ids
+    u32* status;       // [SORT_MAX_PASSES][ntiles][RADIX] decoupled look-back words
+    size_t zero_bytes; // bytes from ghist to the end that must be zeroed before a sort
+    int ntiles;
+    static size_t bytes(int n) {
+        size_t nt = (size_t)(n + SORT_TILE - 1) / SORT_TILE;
+        if (nt == 0) nt = 1;
+        return align_up(SORT_MAX_PASSES * RADIX * sizeof(u32)) + align_up(SORT_MAX_PASSES * sizeof(u32)) +
+               align_up((size_t)SORT_MAX_PASSES * nt * RADIX * sizeof(u32));
+    }
+    static SortScratch from(char*& p, int n) {
+        SortScratch s;
+        char* p0 = p;
+        size_t nt = (size_t)(n + SORT_TILE - 1) / SORT_TILE;
+        if (nt == 0) nt = 1;
+        s.ntiles = (int)nt;
+        carve(p, s.ghist, SORT_MAX_PASSES * RADIX);
+        carve(p, s.tile_counter, SORT_MAX_PASSES);
+        carve(p, s.status, (size_t)SORT_MAX_PASSES * nt * RADIX);
+        s.zero_bytes = (size_t)(p - p0);
+        return s;
+    }
+};
+
+// Per-Gaussian state kept from forward to backward.
+//   rec[3g+0] = {pix.x, pix.y, depth, bits(clamped mask)}   rec[3g+1] = {conic.x, conic.y, conic.z, opacity}
+//   rec[3g+2] = {r, g, b, 0}
+struct GeomState {
+    float4* rec;       // [3P]
+    ushort4* rect;     // [P] {min.x, min.y, width, height} in tiles; width*height == tiles_touched
+    // forward-only temporaries (depth sort ping-pong; after the 4 passes the result is back in key_a / idx_a)
+    u32* key_a;        // [P] float bits of view-space depth, 0xFFFFFFFF when culled
+    u32* key_b;        // [P]
+    u32* idx_a;        // [P] Gaussian ids in (depth, id) order after the sort (culled ones last)
+    u32* idx_b;        // [P]
+    unsigned long long* counters;  // [4]: [0] = total tile instances, [1] = emit tile counter, [2..3] spare
+    u32* emit_status;  // [ceil(P/EMIT_TILE)] chained-scan words of the emit kernel
+    SortScratch sort;
+    static size_t bytes(int P);
+    static GeomState from(char* p, int P);
+};
+
+constexpr int EMIT_THREADS = 256;
+
+// Tile-sort ping-pong: emit fills (tile_buf[0], id_buf[0]); after `npass` passes the sorted data is in buffer npass&1.
+struct BinningState {
+    u32* tile_buf[2];   // [R] tile id of every instance
+    u32* id_buf[2];     // [R] Gaussian id of every instance
+    u32* point_list;    // = id_buf[npass & 1]: ids sorted by (tile, depth, id) -- the only part backward needs
+    u32* tile_sorted;   // = tile_buf[npass & 1]
+    SortScratch sort;
+    static size_t bytes(int R);
+    static BinningState from(char* p, int R, int npass);
+};
+// number of 8-bit passes needed to sort tile ids < ntiles
+inline int tile_sort_bits(int ntiles) {
+    int bits = 1;
+    while ((1 << bits) < ntiles) bits++;
+    return bits;
+}
+inline int tile_sort_passes(int ntiles) { return (tile_sort_bits(ntiles) + RADIX_BITS - 1) / RADIX_BITS; }
+
+struct ImageState {
+    float* final_T;   // [N]
+    u32* n_contrib;   // [N]
+    uint2* ranges;    // [tiles]
+    static size_t bytes(int width, int height);
+    static ImageState from(char* p, int width, int height);
+};
+
+inline int tiles_x(int w) { return (w + TILE_X - 1) / TILE_X; }
+inline int tiles_y(int h) { return (h + TILE_Y - 1) / TILE_Y; }
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------------------------
+struct FwdArgs {
+    int P, D, M, W, H;
+    const float* background;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    const float* shift_factors;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    int prefiltered;
+};
+
+int launch_preprocess_fwd(const FwdArgs& a, GeomState& g, int* radii, float* mean2Dx, float* mean2Dy,
+                          cudaStream_t st);
+int launch_unpack(int P, int R, int W, int H, const GeomState& g, const BinningState& b, const ImageState& img,
+                  u32* tiles_touched, u32* depth_bits, float* xy, float* conic_opacity, float* rgb, u32* point_list,
+                  u64* point_list_keys, u32* ranges, u32* n_contrib, float* final_T, cudaStream_t st);
+int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* vals_out, int begin_bit, int end_bit,
+                      SortScratch& sc, bool iota_vals, cudaStream_t st, u32** final_keys, u32** final_vals);
+int launch_emit(int P, const GeomState& g, const u32* sorted_idx, BinningState& b, int grid_x, cudaStream_t st);
+int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st);
+int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
+                     float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
+int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, const ImageState& img, const float* bg,
+                     const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalpha, float* gacc,
+                     cudaStream_t st);
+
+struct BwdArgs {
+    int P, D, M, W, H;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    const int* radii;
+};
+struct BwdOut {
+    float* dL_dmean2D;
+    float* dL_dmean2D_densify;
+    float* covariance;
+    float* dL_dopacity;
+    float* dL_dcolor;
+    float* dL_dmean3D;
+    float* dL_dcov3D;
+    float* dL_dsh;
+    float* dL_dscale;
+    float* dL_drot;
+    float* dL_dprojmatrix;
+    float* dL_dviewmatrix;
+    float* dL_dcampos;
+    float* dL_dshift;
+};
+// gacc: [P][16] accumulated by blend_bwd; pose_acc: [64] floats + counters, zeroed by the caller.
+int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, float* pose_acc,
+                          const BwdOut& o, cudaStream_t st);
+
+constexpr int GACC_STRIDE = 16;
+// gacc record layout (floats)
+enum { GA_R = 0, GA_G = 1, GA_B = 2, GA_DEPTH = 3, GA_MX = 4, GA_MY = 5, GA_AMX = 6, GA_AMY = 7,
+       GA_CA = 8, GA_CB = 9, GA_CC = 10, GA_OP = 11, GA_COV = 12 };
+
+}  // namespace bags

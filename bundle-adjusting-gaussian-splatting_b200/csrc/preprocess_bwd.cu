@@ -1,0 +1,520 @@
+// Fused backward preprocess for sm_100a: the reference's computeCov2DCUDA (K8) + preprocessCUDA (K9) + the four
+// .mean(0) pose reductions + 16 zero-filled scratch tensors, in one pass over the Gaussians.
+//
+// Restates 3dgs-pose/cuda_rasterizer/backward.cu:37-170 (SH), :175-373 (2D covariance), :377-440 (scale/rotation),
+// :548-922 (projection, depth, pose terms) and rasterize_points.cu:170-185,274 (zeros + .mean(0) + covariance+1e-4),
+// quirks included:
+//   * the 2D covariance is recomputed WITHOUT the entrance-pupil shift, and the SH direction likewise (Q2);
+//   * dL_dmeans3D's projection term carries the extra integer factors (W/2) and (H/2) on top of the NDC-unit
+//     dL_dmean2D (Q9); the projection-matrix gradient does not (Q10: rows 2,6,10,14 stay zero);
+//   * dL_dshift's projection term re-uses theta^3 in the first summand of all three components and is evaluated in
+//     FP64 through the (-1.) literals (Q11);
+//   * pose / intrinsic gradients are means over all P rows, culled rows counting as zero (Q12);
+//   * the reference's dL_dviewmatrix is a data race in which every visible thread overwrites row 0
+//     (backward.cu:351-363); after .mean(0) it is (the 8 terms of one arbitrary visible Gaussian)/P.  We make the
+//     deterministic choice "highest-index visible Gaussian" (Q13).
+//
+// Every dense output row is written here (zeros for culled Gaussians), so the binding allocates with empty().
+// The per-Gaussian P x (16+16+3+3) pose scratch of the reference does not exist: pose terms are reduced per warp /
+// CTA and committed with one atomic per CTA and term.
+#include "../../include/bags_b200.h"
+#include "common.cuh"
+#include "math.cuh"
+
+namespace bags {
+
+constexpr int PB_THREADS = 256;
+// pose_acc layout (floats): [0..15] sum dL_dproj, [16..18] sum dL_dcampos, [19..21] sum dL_dshift,
+// [32] (as u32) 1 + highest visible index
+constexpr int PA_PROJ = 0, PA_CAMPOS = 16, PA_SHIFT = 19, PA_WINNER = 32, PA_NRED = 22;
+
+struct Cov2DBack {
+    float dL_dcov[6];
+    float dL_dT00, dL_dT01, dL_dT02, dL_dT10, dL_dT11, dL_dT12;
+    float dL_dtx, dL_dty, dL_dtz;
+    float tz, tz2;
+};
+
+// backward.cu:195-327 of the reference, for one Gaussian.
+__device__ __forceinline__ Cov2DBack cov2d_backward(const float3 mean, const float* cov3D, float h_x, float h_y,
+                                                    float tan_fovx, float tan_fovy, const float* view_matrix,
+                                                    const float3 dL_dconic) {
+    Cov2DBack o;
+    float3 t = xform4x3(mean, view_matrix);
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, txtz)) * t.z;
+    t.y = min(limy, max(-limy, tytz)) * t.z;
+    const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
+    const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
+
+    M3 J = m3_cols(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z),
+                   0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z),
+                   0.0f, 0.0f, 0.0f);
+    M3 Wm = m3_cols(view_matrix[0], view_matrix[4], view_matrix[8], view_matrix[1], view_matrix[5], view_matrix[9],
+                    view_matrix[2], view_matrix[6], view_matrix[10]);
+    M3 Vrk = m3_cols(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+    M3 T = m3_mul(Wm, J);
+    M3 cov2D = m3_mul(m3_mul(m3_transpose(T), m3_transpose(Vrk)), T);
+
+    const float a = cov2D.c[0][0] + 0.3f;
+    const float b = cov2D.c[0][1];
+    const float c = cov2D.c[1][1] + 0.3f;
+
+    const float denom = a * c - b * b;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+
+    if (denom2inv != 0) {
+        dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+        dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+        dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+
+        o.dL_dcov[0] = (T.c[0][0] * T.c[0][0] * dL_da + T.c[0][0] * T.c[1][0] * dL_db + T.c[1][0] * T.c[1][0] * dL_dc);
+        o.dL_dcov[3] = (T.c[0][1] * T.c[0][1] * dL_da + T.c[0][1] * T.c[1][1] * dL_db + T.c[1][1] * T.c[1][1] * dL_dc);
+        o.dL_dcov[5] = (T.c[0][2] * T.c[0][2] * dL_da + T.c[0][2] * T.c[1][2] * dL_db + T.c[1][2] * T.c[1][2] * dL_dc);
+        o.dL_dcov[1] = 2 * T.c[0][0] * T.c[0][1] * dL_da + (T.c[0][0] * T.c[1][1] + T.c[0][1] * T.c[1][0]) * dL_db +
+                       2 * T.c[1][0] * T.c[1][1] * dL_dc;
+        o.dL_dcov[2] = 2 * T.c[0][0] * T.c[0][2] * dL_da + (T.c[0][0] * T.c[1][2] + T.c[0][2] * T.c[1][0]) * dL_db +
+                       2 * T.c[1][0] * T.c[1][2] * dL_dc;
+        o.dL_dcov[4] = 2 * T.c[0][2] * T.c[0][1] * dL_da + (T.c[0][1] * T.c[1][2] + T.c[0][2] * T.c[1][1]) * dL_db +
+                       2 * T.c[1][1] * T.c[1][2] * dL_dc;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; i++) o.dL_dcov[i] = 0;
+    }
+
+    o.dL_dT00 = 2 * (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_da +
+                (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_db;
+    o.dL_dT01 = 2 * (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_da +
+                (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_db;
+    o.dL_dT02 = 2 * (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_da +
+                (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_db;
+    o.dL_dT10 = 2 * (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_dc +
+                (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_db;
+    o.dL_dT11 = 2 * (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_dc +
+                (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_db;
+    o.dL_dT12 = 2 * (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_dc +
+                (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_db;
+
+    const float dL_dJ00 = Wm.c[0][0] * o.dL_dT00 + Wm.c[0][1] * o.dL_dT01 + Wm.c[0][2] * o.dL_dT02;
+    const float dL_dJ02 = Wm.c[2][0] * o.dL_dT00 + Wm.c[2][1] * o.dL_dT01 + Wm.c[2][2] * o.dL_dT02;
+    const float dL_dJ11 = Wm.c[1][0] * o.dL_dT10 + Wm.c[1][1] * o.dL_dT11 + Wm.c[1][2] * o.dL_dT12;
+    const float dL_dJ12 = Wm.c[2][0] * o.dL_dT10 + Wm.c[2][1] * o.dL_dT11 + Wm.c[2][2] * o.dL_dT12;
+
+    const float tz = 1.f / t.z;
+    const float tz2 = tz * tz;
+    const float tz3 = tz2 * tz;
+    o.tz = tz;
+    o.tz2 = tz2;
+
+    o.dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+    o.dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+    o.dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
+               (2 * h_y * t.y) * tz3 * dL_dJ12;
+    return o;
+}
+
+__device__ __forceinline__ void load_cov3d(int idx, const float* cov3D_precomp, const float* scales,
+                                           const float* rotations, float scale_modifier, float* cov6) {
+    if (cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * (size_t)idx + k];
+    } else {
+        cov3d_from_scale_rot(scales[3 * (size_t)idx], scales[3 * (size_t)idx + 1], scales[3 * (size_t)idx + 2],
+                             scale_modifier, rotations[4 * (size_t)idx], rotations[4 * (size_t)idx + 1],
+                             rotations[4 * (size_t)idx + 2], rotations[4 * (size_t)idx + 3], cov6);
+    }
+}
+
+__global__ void __launch_bounds__(PB_THREADS)
+preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
+                      const float* __restrict__ shs, const float* __restrict__ scales,
+                      const float* __restrict__ rotations, float scale_modifier,
+                      const float* __restrict__ cov3D_precomp, const float* __restrict__ viewmatrix,
+                      const float* __restrict__ projmatrix, const float* __restrict__ campos_ptr, int W, int H,
+                      float tan_fovx, float tan_fovy, float focal_x, float focal_y, const float4* __restrict__ rec,
+                      const float* __restrict__ gacc, float* __restrict__ pose_acc, BwdOut o) {
+    __shared__ float view[16];
+    __shared__ float proj[16];
+    __shared__ float campos[3];
+    __shared__ float s_red[PB_THREADS / 32][PA_NRED];
+    __shared__ u32 s_win[PB_THREADS / 32];
+    if (threadIdx.x < 16) {
+        view[threadIdx.x] = viewmatrix[threadIdx.x];
+        proj[threadIdx.x] = projmatrix[threadIdx.x];
+    }
+    if (threadIdx.x < 3) campos[threadIdx.x] = campos_ptr[threadIdx.x];
+    __syncthreads();
+
+    const int idx = blockIdx.x * PB_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    float pose[PA_NRED];
+#pragma unroll
+    for (int k = 0; k < PA_NRED; k++) pose[k] = 0.f;
+    u32 winner = 0;
+
+    if (idx < P) {
+        const size_t i = (size_t)idx;
+        const bool visible = radii[idx] > 0;
+        float out_mean3D[3] = {0.f, 0.f, 0.f};
+        float out_mean2D[2] = {0.f, 0.f};
+        float out_dens[2] = {0.f, 0.f};
+        float out_color[3] = {0.f, 0.f, 0.f};
+        float out_opacity = 0.f;
+        float out_covariance = 0.0001f;   // zeros + 1e-4 (rasterize_points.cu:274)
+        float out_cov3D[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float out_scale[3] = {0.f, 0.f, 0.f};
+        float out_rot[4] = {0.f, 0.f, 0.f, 0.f};
+
+        if (visible) {
+            winner = (u32)idx + 1u;
+            const float4* ga = reinterpret_cast<const float4*>(gacc + i * GACC_STRIDE);
+            const float4 g0 = ga[0], g1 = ga[1], g2 = ga[2];
+            const float g_cov = gacc[i * GACC_STRIDE + GA_COV];
+            float dL_dcolor[3] = {g0.x, g0.y, g0.z};
+            const float dL_ddepth = g0.w;
+            const float dmx = g1.x, dmy = g1.y;          // dL_dmean2D (NDC units)
+            const float3 dL_dconic = {g2.x, g2.y, g2.z};
+            out_mean2D[0] = dmx; out_mean2D[1] = dmy;
+            out_dens[0] = g1.z; out_dens[1] = g1.w;
+            out_color[0] = g0.x; out_color[1] = g0.y; out_color[2] = g0.z;
+            out_opacity = g2.w;
+            out_covariance = g_cov + 0.0001f;
+
+            const float3 m = {means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]};
+            float cov6[6];
+            load_cov3d(idx, cov3D_precomp, scales, rotations, scale_modifier, cov6);
+
+            // ---- K8: conic -> cov2D -> cov3D / mean ------------------------------------------------------------
+            const Cov2DBack cb = cov2d_backward(m, cov6, focal_x, focal_y, tan_fovx, tan_fovy, view, dL_dconic);
+#pragma unroll
+            for (int k = 0; k < 6; k++) out_cov3D[k] = cb.dL_dcov[k];
+
+            const float4 p_hom = xform4x4(m, proj);
+            const float2 ab = {p_hom.x / p_hom.w, p_hom.y / p_hom.w};
+            const float theta = atan(sqrt(ab.x * ab.x + ab.y * ab.y));
+            const float theta2 = theta * theta;
+            const float theta3 = theta2 * theta;
+            const float theta5 = theta2 * theta3;
+            const float theta7 = theta2 * theta5;
+            float dshift[3] = {cb.dL_dtz * theta3, cb.dL_dtz * theta5, cb.dL_dtz * theta7};
+
+            float3 dL_dmean = xformVec4x3T({cb.dL_dtx, cb.dL_dty, cb.dL_dtz}, view);
+            float dmean[3] = {dL_dmean.x, dL_dmean.y, dL_dmean.z};
+
+            // ---- K9: projection part ---------------------------------------------------------------------------
+            const float4 m_hom = p_hom;
+            const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+            const float scaling_radial = 1.;
+            const int image_width = W, image_height = H;
+            const float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
+            const float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
+            float pm[3];
+            pm[0] = scaling_radial * (image_width / 2) * (proj[0] * m_w - proj[3] * mul1) * dmx +
+                    scaling_radial * (image_height / 2) * (proj[1] * m_w - proj[3] * mul2) * dmy;
+            pm[1] = scaling_radial * (image_width / 2) * (proj[4] * m_w - proj[7] * mul1) * dmx +
+                    scaling_radial * (image_height / 2) * (proj[5] * m_w - proj[7] * mul2) * dmy;
+            pm[2] = scaling_radial * (image_width / 2) * (proj[8] * m_w - proj[11] * mul1) * dmx +
+                    scaling_radial * (image_height / 2) * (proj[9] * m_w - proj[11] * mul2) * dmy;
+
+            // Q11: the first summand uses theta3 in all three components; FP64 through the (-1.) literal.
+            dshift[0] += (float)(dmx * (image_width / 2) * m_hom.x * (-1. / (m_w * m_w)) * theta3 +
+                                 dmy * (image_height / 2) * m_hom.y * (-1. / (m_w * m_w)) * theta3);
+            dshift[1] += (float)(dmx * (image_width / 2) * m_hom.x * (-1. / (m_w * m_w)) * theta3 +
+                                 dmy * (image_height / 2) * m_hom.y * (-1. / (m_w * m_w)) * theta5);
+            dshift[2] += (float)(dmx * (image_width / 2) * m_hom.x * (-1. / (m_w * m_w)) * theta3 +
+                                 dmy * (image_height / 2) * m_hom.y * (-1. / (m_w * m_w)) * theta7);
+
+            pose[PA_PROJ + 0] = scaling_radial * m_w * m.x * dmx;
+            pose[PA_PROJ + 4] = scaling_radial * m_w * m.y * dmx;
+            pose[PA_PROJ + 8] = scaling_radial * m_w * m.z * dmx;
+            pose[PA_PROJ + 12] = scaling_radial * m_w * dmx;
+            pose[PA_PROJ + 1] = scaling_radial * m_w * m.x * dmy;
+            pose[PA_PROJ + 5] = scaling_radial * m_w * m.y * dmy;
+            pose[PA_PROJ + 9] = scaling_radial * m_w * m.z * dmy;
+            pose[PA_PROJ + 13] = scaling_radial * m_w * dmy;
+            pose[PA_PROJ + 3] = scaling_radial * (m_w * m_w * (-1.) * m_hom.x * m.x * dmx +
+                                                  m_w * m_w * (-1.) * m_hom.y * m.x * dmy);
+            pose[PA_PROJ + 7] = scaling_radial * (m_w * m_w * (-1.) * m_hom.x * m.y * dmx +
+                                                  m_w * m_w * (-1.) * m_hom.y * m.y * dmy);
+            pose[PA_PROJ + 11] = scaling_radial * (m_w * m_w * (-1.) * m_hom.x * m.z * dmx +
+                                                   m_w * m_w * (-1.) * m_hom.y * m.z * dmy);
+            pose[PA_PROJ + 15] = scaling_radial * (m_w * m_w * (-1.) * m_hom.x * dmx +
+                                                   m_w * m_w * (-1.) * m_hom.y * dmy);
+
+            dmean[0] += pm[0];
+            dmean[1] += pm[1];
+            dmean[2] += pm[2];
+            // depth -> mean (backward.cu:910-912)
+            dmean[0] += view[2] * dL_ddepth;
+            dmean[1] += view[6] * dL_ddepth;
+            dmean[2] += view[10] * dL_ddepth;
+
+            // ---- SH backward (backward.cu:37-170) --------------------------------------------------------------
+            if (shs) {
+                const u32 clamp_mask = __float_as_uint(rec[3 * i].w);
+                const float3 dir_orig = {m.x - campos[0], m.y - campos[1], m.z - campos[2]};
+                const float len = sqrt(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+                const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+                const float* sh = shs + i * M * 3;
+                float* dsh = o.dL_dsh + i * M * 3;
+                float dRGB[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) dRGB[ch] = dL_dcolor[ch] * ((clamp_mask >> ch) & 1u ? 0 : 1);
+
+                float ddir[3] = {0.f, 0.f, 0.f};  // dL/d(dir) accumulated over channels
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const float g = dRGB[ch];
+                    float dx = 0.f, dy = 0.f, dz = 0.f;
+                    dsh[0 * 3 + ch] = BAGS_SH_C0 * g;
+                    if (D > 0) {
+                        dsh[1 * 3 + ch] = (-BAGS_SH_C1 * y) * g;
+                        dsh[2 * 3 + ch] = (BAGS_SH_C1 * z) * g;
+                        dsh[3 * 3 + ch] = (-BAGS_SH_C1 * x) * g;
+                        dx = -BAGS_SH_C1 * sh[3 * 3 + ch];
+                        dy = -BAGS_SH_C1 * sh[1 * 3 + ch];
+                        dz = BAGS_SH_C1 * sh[2 * 3 + ch];
+                        if (D > 1) {
+                            dsh[4 * 3 + ch] = (BAGS_SH_C2_0 * xy) * g;
+                            dsh[5 * 3 + ch] = (BAGS_SH_C2_1 * yz) * g;
+                            dsh[6 * 3 + ch] = (BAGS_SH_C2_2 * (2.f * zz - xx - yy)) * g;
+                            dsh[7 * 3 + ch] = (BAGS_SH_C2_3 * xz) * g;
+                            dsh[8 * 3 + ch] = (BAGS_SH_C2_4 * (xx - yy)) * g;
+                            const float s4 = sh[4 * 3 + ch], s5 = sh[5 * 3 + ch], s6 = sh[6 * 3 + ch],
+                                        s7 = sh[7 * 3 + ch], s8 = sh[8 * 3 + ch];
+                            dx += BAGS_SH_C2_0 * y * s4 + BAGS_SH_C2_2 * 2.f * -x * s6 + BAGS_SH_C2_3 * z * s7 +
+                                  BAGS_SH_C2_4 * 2.f * x * s8;
+                            dy += BAGS_SH_C2_0 * x * s4 + BAGS_SH_C2_1 * z * s5 + BAGS_SH_C2_2 * 2.f * -y * s6 +
+                                  BAGS_SH_C2_4 * 2.f * -y * s8;
+                            dz += BAGS_SH_C2_1 * y * s5 + BAGS_SH_C2_2 * 2.f * 2.f * z * s6 + BAGS_SH_C2_3 * x * s7;
+                            if (D > 2) {
+                                dsh[9 * 3 + ch] = (BAGS_SH_C3_0 * y * (3.f * xx - yy)) * g;
+                                dsh[10 * 3 + ch] = (BAGS_SH_C3_1 * xy * z) * g;
+                                dsh[11 * 3 + ch] = (BAGS_SH_C3_2 * y * (4.f * zz - xx - yy)) * g;
+                                dsh[12 * 3 + ch] = (BAGS_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy)) * g;
+                                dsh[13 * 3 + ch] = (BAGS_SH_C3_4 * x * (4.f * zz - xx - yy)) * g;
+                                dsh[14 * 3 + ch] = (BAGS_SH_C3_5 * z * (xx - yy)) * g;
+                                dsh[15 * 3 + ch] = (BAGS_SH_C3_6 * x * (xx - 3.f * yy)) * g;
+                                const float s9 = sh[9 * 3 + ch], s10 = sh[10 * 3 + ch], s11 = sh[11 * 3 + ch],
+                                            s12 = sh[12 * 3 + ch], s13 = sh[13 * 3 + ch], s14 = sh[14 * 3 + ch],
+                                            s15 = sh[15 * 3 + ch];
+                                dx += (BAGS_SH_C3_0 * s9 * 3.f * 2.f * xy + BAGS_SH_C3_1 * s10 * yz +
+                                       BAGS_SH_C3_2 * s11 * -2.f * xy + BAGS_SH_C3_3 * s12 * -3.f * 2.f * xz +
+                                       BAGS_SH_C3_4 * s13 * (-3.f * xx + 4.f * zz - yy) +
+                                       BAGS_SH_C3_5 * s14 * 2.f * xz + BAGS_SH_C3_6 * s15 * 3.f * (xx - yy));
+                                dy += (BAGS_SH_C3_0 * s9 * 3.f * (xx - yy) + BAGS_SH_C3_1 * s10 * xz +
+                                       BAGS_SH_C3_2 * s11 * (-3.f * yy + 4.f * zz - xx) +
+                                       BAGS_SH_C3_3 * s12 * -3.f * 2.f * yz + BAGS_SH_C3_4 * s13 * -2.f * xy +
+                                       BAGS_SH_C3_5 * s14 * -2.f * yz + BAGS_SH_C3_6 * s15 * -3.f * 2.f * xy);
+                                dz += (BAGS_SH_C3_1 * s10 * xy + BAGS_SH_C3_2 * s11 * 4.f * 2.f * yz +
+                                       BAGS_SH_C3_3 * s12 * 3.f * (2.f * zz - xx - yy) +
+                                       BAGS_SH_C3_4 * s13 * 4.f * 2.f * xz + BAGS_SH_C3_5 * s14 * (xx - yy));
+                            }
+                        }
+                    }
+                    ddir[0] += dx * g;
+                    ddir[1] += dy * g;
+                    ddir[2] += dz * g;
+                }
+                // coefficients above the active degree get exact zeros (reference: torch::zeros)
+                const int active = (D + 1) * (D + 1);
+                for (int k = active; k < M; k++) {
+                    dsh[k * 3 + 0] = 0.f;
+                    dsh[k * 3 + 1] = 0.f;
+                    dsh[k * 3 + 2] = 0.f;
+                }
+                // normalisation of the direction (auxiliary.h:107-117)
+                const float3 v = dir_orig;
+                const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+                const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+                float3 dm;
+                dm.x = ((+sum2 - v.x * v.x) * ddir[0] - v.y * v.x * ddir[1] - v.z * v.x * ddir[2]) * invsum32;
+                dm.y = (-v.x * v.y * ddir[0] + (sum2 - v.y * v.y) * ddir[1] - v.z * v.y * ddir[2]) * invsum32;
+                dm.z = (-v.x * v.z * ddir[0] - v.y * v.z * ddir[1] + (sum2 - v.z * v.z) * ddir[2]) * invsum32;
+                dmean[0] += dm.x;
+                dmean[1] += dm.y;
+                dmean[2] += dm.z;
+                pose[PA_CAMPOS + 0] = -dm.x;
+                pose[PA_CAMPOS + 1] = -dm.y;
+                pose[PA_CAMPOS + 2] = -dm.z;
+            }
+
+            // ---- cov3D -> scale / rotation (backward.cu:377-440) ----------------------------------------------
+            if (scales) {
+                const float sx0 = scales[3 * i], sy0 = scales[3 * i + 1], sz0 = scales[3 * i + 2];
+                const float r = rotations[4 * i], x = rotations[4 * i + 1], y = rotations[4 * i + 2],
+                            z = rotations[4 * i + 3];
+                M3 R = m3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                               2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                               2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+                M3 S = m3_cols(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
+                const float s0 = scale_modifier * sx0, s1 = scale_modifier * sy0, s2 = scale_modifier * sz0;
+                S.c[0][0] = s0;
+                S.c[1][1] = s1;
+                S.c[2][2] = s2;
+                M3 Mm = m3_mul(S, R);
+                const float* dc = out_cov3D;
+                M3 dL_dSigma = m3_cols(dc[0], 0.5f * dc[1], 0.5f * dc[2], 0.5f * dc[1], dc[3], 0.5f * dc[4],
+                                       0.5f * dc[2], 0.5f * dc[4], dc[5]);
+                M3 dL_dM = m3_mul(m3_scale(2.0f, Mm), dL_dSigma);
+                M3 Rt = m3_transpose(R);
+                M3 dL_dMt = m3_transpose(dL_dM);
+                out_scale[0] = Rt.c[0][0] * dL_dMt.c[0][0] + Rt.c[0][1] * dL_dMt.c[0][1] + Rt.c[0][2] * dL_dMt.c[0][2];
+                out_scale[1] = Rt.c[1][0] * dL_dMt.c[1][0] + Rt.c[1][1] * dL_dMt.c[1][1] + Rt.c[1][2] * dL_dMt.c[1][2];
+                out_scale[2] = Rt.c[2][0] * dL_dMt.c[2][0] + Rt.c[2][1] * dL_dMt.c[2][1] + Rt.c[2][2] * dL_dMt.c[2][2];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    dL_dMt.c[0][k] *= s0;
+                    dL_dMt.c[1][k] *= s1;
+                    dL_dMt.c[2][k] *= s2;
+                }
+                out_rot[0] = 2 * z * (dL_dMt.c[0][1] - dL_dMt.c[1][0]) + 2 * y * (dL_dMt.c[2][0] - dL_dMt.c[0][2]) +
+                             2 * x * (dL_dMt.c[1][2] - dL_dMt.c[2][1]);
+                out_rot[1] = 2 * y * (dL_dMt.c[1][0] + dL_dMt.c[0][1]) + 2 * z * (dL_dMt.c[2][0] + dL_dMt.c[0][2]) +
+                             2 * r * (dL_dMt.c[1][2] - dL_dMt.c[2][1]) - 4 * x * (dL_dMt.c[2][2] + dL_dMt.c[1][1]);
+                out_rot[2] = 2 * x * (dL_dMt.c[1][0] + dL_dMt.c[0][1]) + 2 * r * (dL_dMt.c[2][0] - dL_dMt.c[0][2]) +
+                             2 * z * (dL_dMt.c[1][2] + dL_dMt.c[2][1]) - 4 * y * (dL_dMt.c[2][2] + dL_dMt.c[0][0]);
+                out_rot[3] = 2 * r * (dL_dMt.c[0][1] - dL_dMt.c[1][0]) + 2 * x * (dL_dMt.c[2][0] + dL_dMt.c[0][2]) +
+                             2 * y * (dL_dMt.c[1][2] + dL_dMt.c[2][1]) - 4 * z * (dL_dMt.c[1][1] + dL_dMt.c[0][0]);
+            }
+
+            out_mean3D[0] = dmean[0];
+            out_mean3D[1] = dmean[1];
+            out_mean3D[2] = dmean[2];
+            pose[PA_SHIFT + 0] = dshift[0];
+            pose[PA_SHIFT + 1] = dshift[1];
+            pose[PA_SHIFT + 2] = dshift[2];
+        } else if (o.dL_dsh != nullptr && M > 0) {
+            float* dsh = o.dL_dsh + i * M * 3;
+            for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
+        }
+
+        // dense outputs, every row
+#pragma unroll
+        for (int k = 0; k < 3; k++) o.dL_dmean3D[3 * i + k] = out_mean3D[k];
+        o.dL_dmean2D[3 * i + 0] = out_mean2D[0];
+        o.dL_dmean2D[3 * i + 1] = out_mean2D[1];
+        o.dL_dmean2D[3 * i + 2] = 0.f;
+        o.dL_dmean2D_densify[3 * i + 0] = out_dens[0];
+        o.dL_dmean2D_densify[3 * i + 1] = out_dens[1];
+        o.dL_dmean2D_densify[3 * i + 2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) o.dL_dcolor[3 * i + k] = out_color[k];
+        o.dL_dopacity[i] = out_opacity;
+        o.covariance[i] = out_covariance;
+#pragma unroll
+        for (int k = 0; k < 6; k++) o.dL_dcov3D[6 * i + k] = out_cov3D[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) o.dL_dscale[3 * i + k] = out_scale[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o.dL_drot[4 * i + k] = out_rot[k];
+    }
+
+    // ---- pose terms: warp butterfly -> CTA -> one atomic per term ------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < PA_NRED; k++) {
+        float v = pose[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    const u32 wwin = __reduce_max_sync(0xffffffffu, winner);
+    if (lane == 0) s_win[warp] = wwin;
+    __syncthreads();
+    if (threadIdx.x < PA_NRED) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < PB_THREADS / 32; w++) v += s_red[w][threadIdx.x];
+        if (v != 0.f) atomicAdd(&pose_acc[threadIdx.x], v);
+    }
+    if (threadIdx.x == 32) {
+        u32 m = 0;
+#pragma unroll
+        for (int w = 0; w < PB_THREADS / 32; w++) m = max(m, s_win[w]);
+        if (m) atomicMax(reinterpret_cast<u32*>(pose_acc) + PA_WINNER, m);
+    }
+}
+
+// One small CTA: divide the sums by P and evaluate the view-matrix terms of the winning Gaussian.
+__global__ void pose_finalize_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ scales,
+                                     const float* __restrict__ rotations, float scale_modifier,
+                                     const float* __restrict__ cov3D_precomp, const float* __restrict__ viewmatrix,
+                                     float tan_fovx, float tan_fovy, float focal_x, float focal_y,
+                                     const float* __restrict__ gacc, const float* __restrict__ pose_acc, BwdOut o) {
+    const int t = threadIdx.x;
+    const float invP = (float)P;
+    if (t < 16) o.dL_dprojmatrix[t] = pose_acc[PA_PROJ + t] / invP;
+    if (t < 3) {
+        o.dL_dcampos[t] = pose_acc[PA_CAMPOS + t] / invP;
+        o.dL_dshift[t] = pose_acc[PA_SHIFT + t] / invP;
+    }
+    if (t == 0) {
+        float vm[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) vm[k] = 0.f;
+        const u32 win = reinterpret_cast<const u32*>(pose_acc)[PA_WINNER];
+        if (win) {
+            const int idx = (int)win - 1;
+            const size_t i = (size_t)idx;
+            const float3 mean = {means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]};
+            float cov6[6];
+            load_cov3d(idx, cov3D_precomp, scales, rotations, scale_modifier, cov6);
+            const float* ga = gacc + i * GACC_STRIDE;
+            const float3 dL_dconic = {ga[GA_CA], ga[GA_CB], ga[GA_CC]};
+            const float dL_ddepth = ga[GA_DEPTH];
+            const float* view_matrix = viewmatrix;
+            const Cov2DBack cb = cov2d_backward(mean, cov6, focal_x, focal_y, tan_fovx, tan_fovy, view_matrix,
+                                                dL_dconic);
+            const float h_x = focal_x, h_y = focal_y, tz = cb.tz, tz2 = cb.tz2;
+            const float dL_dT00 = cb.dL_dT00, dL_dT01 = cb.dL_dT01, dL_dT02 = cb.dL_dT02;
+            const float dL_dT10 = cb.dL_dT10, dL_dT11 = cb.dL_dT11, dL_dT12 = cb.dL_dT12;
+            // backward.cu:351-363
+            vm[0] = h_x * tz * dL_dT00;
+            vm[1] = h_x * tz * dL_dT01;
+            vm[4] = h_y * tz * dL_dT10;
+            vm[5] = h_y * tz * dL_dT11;
+            vm[2] = -(view_matrix[0] * dL_dT00 + view_matrix[1] * dL_dT01) * mean.x * h_x * tz2 -
+                    (view_matrix[4] * dL_dT10 + view_matrix[5] * dL_dT11 + view_matrix[6] * dL_dT12) * mean.x * h_y * tz2 +
+                    (tz - view_matrix[2] * mean.x) * h_x * tz2 * dL_dT02;
+            vm[6] = -(view_matrix[0] * dL_dT00 + view_matrix[1] * dL_dT01 + view_matrix[2] * dL_dT02) * mean.y * h_x * tz2 -
+                    (view_matrix[4] * dL_dT10 + view_matrix[5] * dL_dT11) * mean.y * h_y * tz2 +
+                    (tz - view_matrix[6] * mean.y) * h_y * tz2 * dL_dT12;
+            vm[10] = -((view_matrix[0] * dL_dT00 + view_matrix[1] * dL_dT01 + view_matrix[2] * dL_dT02) * h_x +
+                       (view_matrix[4] * dL_dT10 + view_matrix[5] * dL_dT11 + view_matrix[6] * dL_dT12) * h_y) *
+                     mean.z * tz2;
+            vm[14] = -((view_matrix[0] * dL_dT00 + view_matrix[1] * dL_dT01 + view_matrix[2] * dL_dT02) * h_x +
+                       (view_matrix[4] * dL_dT10 + view_matrix[5] * dL_dT11 + view_matrix[6] * dL_dT12) * h_y) *
+                     tz2;
+            vm[2] += mean.x * dL_ddepth;
+            vm[6] += mean.y * dL_ddepth;
+            vm[10] += mean.z * dL_ddepth;
+            vm[14] += dL_ddepth;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) o.dL_dviewmatrix[k] = vm[k] / invP;
+    }
+}
+
+int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, float* pose_acc, const BwdOut& o,
+                          cudaStream_t st) {
+    const int blocks = (a.P + PB_THREADS - 1) / PB_THREADS;
+    preprocess_bwd_kernel<<<blocks, PB_THREADS, 0, st>>>(
+        a.P, a.D, a.M, a.means3D, a.radii, a.shs, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp,
+        a.viewmatrix, a.projmatrix, a.campos, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, g.rec, gacc,
+        pose_acc, o);
+    BAGS_LAUNCH_OK("preprocess_bwd_kernel");
+    pose_finalize_kernel<<<1, 32, 0, st>>>(a.P, a.means3D, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp,
+                                           a.viewmatrix, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, gacc,
+                                           pose_acc, o);
+    BAGS_LAUNCH_OK("pose_finalize_kernel");
+    return 0;
+}
+
+}  // namespace bags

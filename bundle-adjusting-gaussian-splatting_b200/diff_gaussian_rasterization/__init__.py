@@ -1,0 +1,151 @@
+"""Drop-in ``diff_gaussian_rasterization`` for Self-Cali-GS / Bundle-Adjusting-Gaussian-Splatting on B200.
+
+Public surface and semantics follow 3dgs-pose/diff_gaussian_rasterization/__init__.py of the reference:
+
+* ``GaussianRasterizationSettings`` -- the 14-field NamedTuple (reference lines 220-234);
+* ``GaussianRasterizer(raster_settings)`` -- ``forward(means3D, means2D, means2D_densify, shift_factors, opacities,
+  shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None)`` returning
+  ``(color, radii, depth, weights, mean2D)`` and ``markVisible(positions)`` (lines 236-287);
+* ``rasterize_gaussians(...)`` (lines 21-49) and ``compute_relocation(...)`` (lines 289-291).
+
+The autograd function returns the 14 gradients in input order, with the view-matrix / camera-centre / projection /
+pupil-shift gradients that ``--opt_cam`` and ``--opt_intrinsic`` consume (reference lines 119-218).
+``gaussian_renderer/__init__.py:render()`` of the reference runs on top of this unchanged.
+
+The native work happens in ``libbags_b200.so`` (hand-written sm_100a kernels, C ABI in include/bags_b200.h)
+reached through ``_C``; there is no CPU path.
+"""
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _C
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    intrinsic: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    debug_iter: int
+
+
+def rasterize_gaussians(means3D, means2D, means2D_densify, shift_factors, sh, colors_precomp, opacities, scales,
+                        rotations, cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(
+        means3D, means2D, means2D_densify, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+        raster_settings.viewmatrix, raster_settings.campos, raster_settings.projmatrix, shift_factors,
+        raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, means2D_densify, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, world_view, camera_center, full_proj, shift_factors, raster_settings):
+        rs = raster_settings
+        args = (rs.bg, means3D, shift_factors, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                cov3Ds_precomp, world_view, full_proj, rs.intrinsic, rs.tanfovx, rs.tanfovy, rs.image_height,
+                rs.image_width, sh, rs.sh_degree, camera_center, rs.prefiltered, rs.debug)
+        if rs.debug:
+            # (the reference's debug branch unpacks the wrong tuple arity and cannot run; this one works)
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                out = _C.rasterize_gaussians(*args)
+            except Exception:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
+        else:
+            out = _C.rasterize_gaussians(*args)
+        num_rendered, color, depth, weights, radii, geomBuffer, binningBuffer, imgBuffer, means2Dx, means2Dy = out
+
+        mean2D = torch.cat((means2Dx, means2Dy), dim=-1)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.camera_center = camera_center
+        ctx.full_proj = full_proj
+        ctx.world_view = world_view
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+                              binningBuffer, imgBuffer, weights)
+        return color, radii, depth, weights, mean2D
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _, grad_out_depth, grad_out_weight, grad_mean2D):
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer,
+         weights) = ctx.saved_tensors
+        args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                ctx.world_view, ctx.full_proj, rs.intrinsic, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width,
+                grad_out_color, grad_out_depth, grad_out_weight, sh, rs.sh_degree, ctx.camera_center, geomBuffer,
+                ctx.num_rendered, binningBuffer, imgBuffer, weights, rs.debug)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                out = _C.rasterize_gaussians_backward(*args)
+            except Exception:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise
+        else:
+            out = _C.rasterize_gaussians_backward(*args)
+        (grad_means2D, grad_means2D_densify, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp,
+         grad_sh, grad_scales, grad_rotations, grad_camera_center, grad_full_proj, grad_world_view,
+         grad_shift_factors, covariance) = out
+
+        grad_full_proj = grad_full_proj[:, None].reshape(4, 4)
+        grad_world_view = grad_world_view[:, None].reshape(4, 4)
+
+        return (grad_means3D, grad_means2D, grad_means2D_densify, grad_sh, grad_colors_precomp, grad_opacities,
+                grad_scales, grad_rotations, grad_cov3Ds_precomp, grad_world_view, grad_camera_center,
+                grad_full_proj, grad_shift_factors, None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, means2D, means2D_densify, shift_factors, opacities, shs=None, colors_precomp=None,
+                scales=None, rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        return rasterize_gaussians(means3D, means2D, means2D_densify, shift_factors, shs, colors_precomp, opacities,
+                                   scales, rotations, cov3D_precomp, rs)
+
+
+def compute_relocation(opacity_old, scale_old, N, binoms, n_max):
+    new_opacity, new_scale = _C.compute_relocation(opacity_old, scale_old, N.int(), binoms, n_max)
+    return new_opacity, new_scale

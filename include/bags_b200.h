@@ -1,0 +1,171 @@
+/*
+ * bags_b200.h -- C ABI of the B200-native (sm_100a) bundle-adjusting Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for the reference's native hot path.  Every entry point takes plain device
+ * pointers, sizes and a cudaStream_t (passed as void*); there are no torch / pybind types in any signature.
+ * Each function names the reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   bags_rasterize_forward        <- CudaRasterizer::Rasterizer::forward   3dgs-pose/cuda_rasterizer/rasterizer.h:31-60
+ *                                    (called from RasterizeGaussiansCUDA,  3dgs-pose/rasterize_points.cu:36-128)
+ *   bags_rasterize_backward       <- CudaRasterizer::Rasterizer::backward  3dgs-pose/cuda_rasterizer/rasterizer.h:62-102
+ *                                    + the four .mean(0) reductions and "covariance + 1e-4" of
+ *                                    RasterizeGaussiansBackwardCUDA,        3dgs-pose/rasterize_points.cu:130-276
+ *   bags_mark_visible             <- CudaRasterizer::Rasterizer::markVisible rasterizer.h:24-29, rasterize_points.cu:278-297
+ *   bags_compute_relocation       <- UTILS::ComputeRelocation              3dgs-pose/cuda_rasterizer/utils.h, utils.cu:6-51
+ *   bags_knn_mean_dist2           <- SimpleKNN::knn                        simple-knn/simple_knn.cu:185-221 (distCUDA2, spatial.cu:14-26)
+ *   bags_unpack_state             (test-only) exposes the private binning/image state so parity tests can compare
+ *                                  tiles_touched / sorted keys / point list / ranges / n_contrib / final_T bit for bit
+ *                                  with the reference's GeometryState/BinningState/ImageState (rasterizer_impl.h:21-72).
+ *
+ * All matrices use the reference's convention: 16 floats, flat index m[4*c + r] (the transposed, row-vector form that
+ * scene/cameras.py hands to GaussianRasterizationSettings).  All tensors are fp32 and contiguous unless stated.
+ * Return value: >= 0 on success, a negative BAGS_E_* code on failure (bags_last_error() gives the text).
+ */
+#ifndef BAGS_B200_H_INCLUDED
+#define BAGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAGS_E_INVALID   (-1)   /* bad argument (null pointer, negative size, unsupported mode) */
+#define BAGS_E_CUDA      (-2)   /* a CUDA runtime call or kernel launch failed                   */
+#define BAGS_E_ALLOC     (-3)   /* an allocation callback returned NULL                          */
+#define BAGS_E_OVERFLOW  (-4)   /* tile-instance count does not fit the 30-bit sort bookkeeping  */
+
+/* Scratch-buffer allocation callback: must return a device pointer to at least `bytes` bytes, 256-byte aligned,
+ * valid until the matching backward call.  Mirrors std::function<char*(size_t)> of rasterizer.h:32-34. */
+typedef char* (*bags_alloc_fn)(size_t bytes, void* user);
+
+const char* bags_last_error(void);
+int bags_version(void);
+
+/* Sizes of the opaque state buffers (bytes).  geom/image depend only on P / W*H; binning needs num_rendered. */
+size_t bags_geom_bytes(int P);
+size_t bags_image_bytes(int width, int height);
+size_t bags_binning_bytes(int P, int num_rendered, int width, int height);
+size_t bags_backward_scratch_bytes(int P);
+
+/* Forward: preprocess -> depth sort -> scan -> emit (tile,id) -> tile sort -> ranges -> blend.
+ * Optional inputs are selected by NULL exactly like the reference (shs vs colors_precomp, scales+rotations vs
+ * cov3D_precomp).  Outputs: out_color [3,H,W], out_depth [H,W], out_alpha [H,W], radii [P] (int32),
+ * mean2Dx/mean2Dy [P] (= p_hom.z / shifted p_hom.w, forward.cu:650-651).  Every output element is written
+ * (no pre-zeroing needed).  Returns num_rendered. */
+int bags_rasterize_forward(
+    bags_alloc_fn geom_alloc, void* geom_user,
+    bags_alloc_fn binning_alloc, void* binning_user,
+    bags_alloc_fn image_alloc, void* image_user,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* intrinsic,
+    const float* cam_pos,
+    const float* shift_factors,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_depth,
+    float* out_alpha,
+    int* radii,
+    float* mean2Dx,
+    float* mean2Dy,
+    int debug,
+    void* stream);
+
+/* Backward.  Dense per-Gaussian outputs ([P,...], every row written, zero for culled Gaussians):
+ *   dL_dmean2D [P,3], dL_dmean2D_densify [P,3], dL_dcolor [P,3], dL_dopacity [P], dL_dmean3D [P,3],
+ *   dL_dcov3D [P,6], dL_dsh [P,M,3] (may be NULL when M == 0), dL_dscale [P,3], dL_drot [P,4], covariance [P]
+ *   (= accumulated conic trace + 1e-4, rasterize_points.cu:274).
+ * Pose / intrinsic outputs, already reduced as mean over all P rows like the reference's .mean(0):
+ *   dL_dcampos [3], dL_dprojmatrix [16], dL_dviewmatrix [16], dL_dshift [3].
+ * `scratch` must hold bags_backward_scratch_bytes(P) bytes (contents undefined on entry). */
+int bags_rasterize_backward(
+    int P, int D, int M, int R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* alphas,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* intrinsic,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    const char* geom_buffer,
+    const char* binning_buffer,
+    const char* image_buffer,
+    const float* dL_dpix,
+    const float* dL_dpix_depth,
+    const float* dL_dalpha,
+    char* scratch,
+    float* dL_dmean2D,
+    float* dL_dmean2D_densify,
+    float* covariance,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    float* dL_dprojmatrix,
+    float* dL_dviewmatrix,
+    float* dL_dcampos,
+    float* dL_dshift,
+    int debug,
+    void* stream);
+
+/* present[i] = (view * p_i).z > 0.2  (auxiliary.h:139-164).  `present` is one byte per point. */
+int bags_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                      uint8_t* present, void* stream);
+
+/* MCMC relocation, Eq. (9) (utils.cu:6-36).  binoms is [n_max, n_max]. */
+int bags_compute_relocation(int P, const float* opacity_old, const float* scale_old, const int* N,
+                            const float* binoms, int n_max, float* opacity_new, float* scale_new, void* stream);
+
+/* Mean squared distance to the 3 nearest neighbours (simple_knn.cu:132-221).  `scratch` must hold
+ * bags_knn_scratch_bytes(P) bytes. */
+size_t bags_knn_scratch_bytes(int P);
+int bags_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scratch, void* stream);
+
+/* Test-only view of the private state.  Any output pointer may be NULL.  All outputs are device pointers:
+ *   tiles_touched [P] u32, depth_bits [P] u32 (float bits of the view-space depth, undefined for culled),
+ *   xy [P,2] f32, conic_opacity [P,4] f32, rgb [P,3] f32,
+ *   point_list [R] u32, point_list_keys [R] u64 (tile << 32 | depth bits, reconstructed), ranges [tiles,2] u32,
+ *   n_contrib [H*W] u32, final_T [H*W] f32. */
+int bags_unpack_state(int P, int R, int width, int height,
+                      const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+                      uint32_t* tiles_touched, uint32_t* depth_bits, float* xy, float* conic_opacity, float* rgb,
+                      uint32_t* point_list, uint64_t* point_list_keys, uint32_t* ranges,
+                      uint32_t* n_contrib, float* final_T, void* stream);
+
+/* Stand-alone access to the hand-written onesweep radix sort (u32 keys, u32 values, bits [begin_bit, end_bit)),
+ * used by tests and micro-benchmarks.  `scratch` must hold bags_sort_scratch_bytes(n) bytes.  keys_in/vals_in are
+ * clobbered (ping-pong); the sorted result is always left in keys_out/vals_out. */
+size_t bags_sort_scratch_bytes(int n);
+int bags_sort_pairs_u32(int n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                        int begin_bit, int end_bit, char* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAGS_B200_H_INCLUDED */

@@ -1,0 +1,206 @@
+"""Shared helpers of the parity tests: load our package and the reference build side by side, run one view
+forward+backward through the public API, and pull out every comparable quantity (including the private integer state
+of both implementations)."""
+import importlib
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "bundle-adjusting-gaussian-splatting_b200")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+import bags_synth as S  # noqa: E402
+
+
+def load_ours():
+    return importlib.import_module("diff_gaussian_rasterization")
+
+
+_ref_mod = None
+
+
+def ref_available():
+    return os.path.exists(os.path.join(REF_DIR, "diff_gaussian_rasterization", "_C.so"))
+
+
+def load_ref():
+    """The unmodified reference extension built by oracle/build_ref.py, imported under another module name."""
+    global _ref_mod
+    if _ref_mod is None:
+        d = os.path.join(REF_DIR, "diff_gaussian_rasterization")
+        spec = importlib.util.spec_from_file_location("ref_dgr", os.path.join(d, "__init__.py"),
+                                                      submodule_search_locations=[d])
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["ref_dgr"] = m
+        spec.loader.exec_module(m)
+        _ref_mod = m
+    return _ref_mod
+
+
+def align(x, a=128):
+    return (x + a - 1) // a * a
+
+
+def parse_ref_state(P, R, H, W, geom, binning, img):
+    """Reads the reference's opaque buffers with the layout of GeometryState / BinningState / ImageState::fromChunk
+    (rasterizer_impl.cu:155-194, rasterizer_impl.h:21-72): every field 128-byte aligned."""
+    g = geom.cpu().numpy()
+    b = binning.cpu().numpy()
+    im = img.cpu().numpy()
+    N = H * W
+    out = {}
+    off = 0
+    out["depths"] = g[off:off + 4 * P].view(np.float32).copy(); off = align(off + 4 * P)
+    out["clamped"] = g[off:off + 3 * P].copy().reshape(P, 3); off = align(off + 3 * P)
+    off = align(off + 4 * P)                                              # internal_radii
+    out["xy"] = g[off:off + 8 * P].view(np.float32).copy().reshape(P, 2); off = align(off + 8 * P)
+    out["cov3D"] = g[off:off + 24 * P].view(np.float32).copy().reshape(P, 6); off = align(off + 24 * P)
+    out["conic_opacity"] = g[off:off + 16 * P].view(np.float32).copy().reshape(P, 4); off = align(off + 16 * P)
+    out["rgb"] = g[off:off + 12 * P].view(np.float32).copy().reshape(P, 3); off = align(off + 12 * P)
+    out["tiles_touched"] = g[off:off + 4 * P].view(np.uint32).copy()
+    off = 0
+    out["final_T"] = im[off:off + 4 * N].view(np.float32).copy(); off = align(off + 4 * N)
+    out["n_contrib"] = im[off:off + 4 * N].view(np.uint32).copy(); off = align(off + 4 * N)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    out["ranges"] = im[off:off + 8 * tiles].view(np.uint32).copy().reshape(tiles, 2)
+    off = 0
+    out["point_list"] = b[off:off + 4 * R].view(np.uint32).copy(); off = align(off + 4 * R)
+    off = align(off + 4 * R)                                              # point_list_unsorted
+    out["point_list_keys"] = b[off:off + 8 * R].view(np.uint64).copy()
+    return out
+
+
+def to_dev(x, dev):
+    return x.to(dev) if isinstance(x, torch.Tensor) else x
+
+
+def run_view(mod, cam, gs, upstream, dev, sh_degree=3, bg=(0.0, 0.0, 0.0), shift=(0.0, 0.0, 0.0),
+             use_colors_precomp=False, use_cov_precomp=False, scale_modifier=1.0, backward=True,
+             colors_precomp=None, cov3D_precomp=None):
+    """One forward(+backward) through the public GaussianRasterizer API of `mod`.  Returns a dict of CPU tensors."""
+    H, W = cam.H, cam.W
+    leaf = lambda t: t.to(dev).clone().requires_grad_(True)
+    means3D = leaf(gs.means3D)
+    opac = leaf(gs.opacities)
+    view = leaf(cam.viewmatrix)
+    proj = leaf(cam.projmatrix)
+    campos = leaf(cam.campos)
+    shift_t = leaf(torch.tensor(shift, dtype=torch.float32))
+    means2D = torch.zeros_like(means3D, requires_grad=True)
+    means2D_d = torch.zeros_like(means3D, requires_grad=True)
+    kw = {}
+    leaves = dict(means3D=means3D, opacities=opac, viewmatrix=view, projmatrix=proj, campos=campos,
+                  shift_factors=shift_t, means2D=means2D, means2D_densify=means2D_d)
+    if use_colors_precomp:
+        c = leaf(colors_precomp)
+        kw["colors_precomp"] = c
+        leaves["colors_precomp"] = c
+    else:
+        s = leaf(gs.shs)
+        kw["shs"] = s
+        leaves["shs"] = s
+    if use_cov_precomp:
+        c3 = leaf(cov3D_precomp)
+        kw["cov3D_precomp"] = c3
+        leaves["cov3D_precomp"] = c3
+    else:
+        sc = leaf(gs.scales)
+        ro = leaf(gs.rotations)
+        kw["scales"] = sc
+        kw["rotations"] = ro
+        leaves["scales"] = sc
+        leaves["rotations"] = ro
+
+    settings = mod.GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.tensor(bg, dtype=torch.float32, device=dev), scale_modifier=scale_modifier,
+        viewmatrix=view, projmatrix=proj, intrinsic=cam.intrinsic.to(dev), sh_degree=sh_degree, campos=campos,
+        prefiltered=False, debug=False, debug_iter=0)
+    rast = mod.GaussianRasterizer(raster_settings=settings)
+    color, radii, depth, weights, mean2D = rast(means3D=means3D, means2D=means2D, means2D_densify=means2D_d,
+                                                shift_factors=shift_t, opacities=opac, **kw)
+    out = {"color": color, "radii": radii, "depth": depth, "weights": weights, "mean2D": mean2D}
+    fn = color.grad_fn
+    P = means3D.shape[0]
+    saved = fn.saved_tensors
+    geomB, binB, imgB = saved[7], saved[8], saved[9]
+    R = fn.num_rendered
+    out["num_rendered"] = R
+    if mod.__name__ == "ref_dgr":
+        st = parse_ref_state(P, R, H, W, geomB, binB, imgB)
+        out["state"] = {k: torch.from_numpy(v.astype(np.int64) if v.dtype in (np.uint32,) else
+                                            (v.view(np.int64) if v.dtype == np.uint64 else v)) for k, v in st.items()}
+    else:
+        st = mod._C.unpack_state(P, R, H, W, geomB, binB, imgB)
+        d = {}
+        for k, v in st.items():
+            v = v.cpu()
+            if v.dtype == torch.int32 and k != "depth_bits":
+                v = v.to(torch.int64) & 0xFFFFFFFF
+            d[k] = v
+        out["state"] = d
+    if backward:
+        dc, dd, da = [u.to(dev) for u in upstream]
+        loss = (color * dc).sum() + (depth * dd).sum() + (weights * da).sum()
+        loss.backward()
+        out["grads"] = {k: (v.grad.detach().cpu() if v.grad is not None else None) for k, v in leaves.items()}
+    res = {}
+    for k, v in out.items():
+        if isinstance(v, torch.Tensor):
+            res[k] = v.detach().cpu()
+        else:
+            res[k] = v
+    return res
+
+
+def rel_l2(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    d = (a - b).norm()
+    n = b.norm()
+    return float(d / n) if n > 0 else float(d)
+
+
+def compare(ours, ref, verbose=True):
+    """Returns a dict of metrics comparing two run_view() results."""
+    m = {}
+    m["num_rendered"] = (ours["num_rendered"], ref["num_rendered"])
+    m["radii_mismatch"] = int((ours["radii"] != ref["radii"]).sum())
+    so, sr = ours["state"], ref["state"]
+    vis = ref["radii"] > 0
+    m["tiles_touched_mismatch"] = int((so["tiles_touched"] != sr["tiles_touched"]).sum())
+    if ours["num_rendered"] == ref["num_rendered"]:
+        m["point_list_mismatch"] = int((so["point_list"] != sr["point_list"]).sum())
+        m["keys_mismatch"] = int((so["point_list_keys"] != sr["point_list_keys"]).sum())
+    else:
+        m["point_list_mismatch"] = m["keys_mismatch"] = -1
+    m["ranges_mismatch"] = int((so["ranges"] != sr["ranges"]).sum())
+    m["n_contrib_mismatch"] = int((so["n_contrib"] != sr["n_contrib"]).sum())
+    m["final_T_maxabs"] = float((so["final_T"] - sr["final_T"]).abs().max())
+    for k in ("xy", "conic_opacity", "rgb"):
+        a, b = so[k][vis], sr[k][vis]
+        m[k + "_maxabs"] = float((a - b).abs().max()) if a.numel() else 0.0
+        m[k + "_bit_mismatch"] = int((a.view(torch.int32) != b.view(torch.int32)).sum()) if a.numel() else 0
+    for k in ("color", "depth", "weights", "mean2D"):
+        m[k + "_maxabs"] = float((ours[k] - ref[k]).abs().max())
+    if "grads" in ours and "grads" in ref:
+        for k, g in ref["grads"].items():
+            go = ours["grads"].get(k)
+            if g is None and go is None:
+                continue
+            if g is None or go is None:
+                m["grad_" + k] = "missing:%s/%s" % (go is None, g is None)
+                continue
+            if k == "viewmatrix":
+                continue
+            m["grad_" + k + "_rel_l2"] = rel_l2(go, g)
+    if verbose:
+        for k, v in m.items():
+            print(f"    {k}: {v}")
+    return m
