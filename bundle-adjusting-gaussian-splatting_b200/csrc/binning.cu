@@ -319,27 +319,32 @@ emit_instances_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* 
     const u32 wtotal = __shfl_sync(0xffffffffu, inc, 31);
     const u32 packed_min = (u32)r.x | ((u32)r.y << 16);
     const u32 width = r.z;
-    for (u32 s = lane; s < wtotal; s += 32) {
-        const u32 slot = wstart + s;
+    // NB: the loop trip count is warp-uniform; every lane takes part in the shuffles and only the stores are guarded.
+    for (u32 sbase = 0; sbase < wtotal; sbase += 32) {
+        const u32 s = sbase + lane;
+        const bool active = s < wtotal;
+        const u32 slot = wstart + (active ? s : 0u);
         // largest lane k with start_k <= slot (starts are non-decreasing)
         int lo = 0;
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
-            int cand = lo + step;
-            u32 sk = __shfl_sync(0xffffffffu, start, cand & 31);
-            if (cand < 32 && sk <= slot) lo = cand;
+            const int cand = lo + step;   // <= 31
+            const u32 sk = __shfl_sync(0xffffffffu, start, cand);
+            if (sk <= slot) lo = cand;
         }
-        // zero-count lanes share their start with the next lane; `lo` is the last of them, which may be empty only if
-        // every later lane is empty too -- impossible while slot < wstart + wtotal.
+        // zero-count lanes share their start with the next lane; the search lands on the last lane of such a run,
+        // which is the non-empty owner because slot < wstart + wtotal.
         const u32 ostart = __shfl_sync(0xffffffffu, start, lo);
         const u32 omin = __shfl_sync(0xffffffffu, packed_min, lo);
         const u32 ow = __shfl_sync(0xffffffffu, width, lo);
         const u32 og = __shfl_sync(0xffffffffu, g, lo);
-        const u32 local = slot - ostart;
-        const u32 ty = (omin >> 16) + local / ow;
-        const u32 tx = (omin & 0xFFFFu) + local % ow;
-        tile_out[slot] = ty * (u32)grid_x + tx;
-        id_out[slot] = og;
+        if (active) {
+            const u32 local = slot - ostart;
+            const u32 ty = (omin >> 16) + local / ow;
+            const u32 tx = (omin & 0xFFFFu) + local % ow;
+            tile_out[slot] = ty * (u32)grid_x + tx;
+            id_out[slot] = og;
+        }
     }
 }
 
