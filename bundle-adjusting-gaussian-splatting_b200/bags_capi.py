@@ -49,9 +49,25 @@ SIGNATURES = {
     "bags_knn_mean_dist2": (c_int, [c_int, _P, _P, _P, _P]),
     "bags_unpack_state": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bags_launch_count": (ctypes.c_ulonglong, []),
+    "bags_profile_enable": (c_int, [c_int]),
+    "bags_profile_read": (c_int, [_P, _P]),
     "bags_sort_scratch_bytes": (c_size_t, [c_int]),
     "bags_sort_pairs_u32": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
 }
+
+
+STAGES = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges", "blend_fwd", "bwd_clear", "blend_bwd",
+          "preprocess_bwd"]
+
+
+def profile_read():
+    """Returns ({stage: total_ms}, {stage: calls}) accumulated since the last read."""
+    n = len(STAGES)
+    ms = (ctypes.c_double * n)()
+    calls = (ctypes.c_ulonglong * n)()
+    check(lib().bags_profile_read(ms, calls), "bags_profile_read")
+    return {STAGES[i]: ms[i] for i in range(n)}, {STAGES[i]: int(calls[i]) for i in range(n)}
 
 
 class BagsError(RuntimeError):

@@ -1,0 +1,83 @@
+"""View-batched data parallelism for the rasterizer.
+
+The reference trains on ONE view per iteration on one GPU and has no distributed code at all.  The natural sharding
+axis is the view: every (view) forward+backward is independent given replicated Gaussian parameters, and the only
+coupling is the sum of the Gaussian-parameter gradients.  This module provides exactly that and nothing more:
+
+* ``shard_views(num_views, rank, world)``  -- rank r of G owns views r, r+G, ...
+* ``FlatGaussianParams``  -- the Gaussian parameters as views into ONE contiguous fp32 buffer (59 floats per Gaussian:
+  means3D 3 | SH 48 | opacity 1 | scales 3 | rotations 4) with ``.grad`` views into ONE contiguous gradient buffer, so
+  autograd accumulates every view's gradients in place and a single all-reduce moves them (no pack step).
+* ``allreduce_gradients(params, group)``  -- one ``all_reduce(SUM)`` over that buffer (NCCL over NVLink on GPUs,
+  gloo in the CPU tests).  Per-camera pose / intrinsic gradients are NOT reduced: each camera is owned by one rank.
+
+Parity definition: the reduced buffer equals the sum over all views of the single-view gradients.
+"""
+from typing import Callable, Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+FIELDS = (("means3D", (3,)), ("shs", (16, 3)), ("opacities", (1,)), ("scales", (3,)), ("rotations", (4,)))
+FLOATS_PER_GAUSSIAN = 59
+
+
+def shard_views(num_views: int, rank: int, world: int) -> List[int]:
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"invalid rank/world {rank}/{world}")
+    return list(range(rank, num_views, world))
+
+
+class FlatGaussianParams:
+    """Gaussian parameters and their gradients in two flat buffers (field-major: all means, then all SH, ...)."""
+
+    def __init__(self, means3D, shs, opacities, scales, rotations, device=None):
+        src = dict(means3D=means3D, shs=shs, opacities=opacities, scales=scales, rotations=rotations)
+        P = means3D.shape[0]
+        device = device if device is not None else means3D.device
+        self.P = P
+        self.flat = torch.empty(P * FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.params = {}
+        off = 0
+        for name, shape in FIELDS:
+            n = P
+            for s in shape:
+                n *= s
+            view = self.flat[off:off + n].view(P, *shape)
+            view.copy_(src[name].reshape(P, *shape))
+            p = view.detach().requires_grad_(True)          # leaf sharing storage with the flat buffer
+            p.grad = self.flat_grad[off:off + n].view(P, *shape)
+            self.params[name] = p
+            off += n
+        assert off == P * FLOATS_PER_GAUSSIAN
+
+    def __getitem__(self, k):
+        return self.params[k]
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+
+def allreduce_gradients(params: FlatGaussianParams, group=None, async_op: bool = False):
+    """Sums the flat gradient buffer over all ranks (no-op without an initialised process group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def run_views(params: FlatGaussianParams, views: Sequence, view_loss: Callable, num_views_total: int = None,
+              rank: int = 0, world: int = 1, group=None):
+    """Gradient accumulation over this rank's share of `views`, then one all-reduce.
+
+    `view_loss(params, view) -> scalar loss tensor` renders one view and returns its loss; per-view pose gradients
+    land on that view's own leaves.  Returns the list of local losses (python floats are NOT taken: no host sync).
+    """
+    n = len(views) if num_views_total is None else num_views_total
+    losses = []
+    for vi in shard_views(n, rank, world):
+        loss = view_loss(params, views[vi])
+        loss.backward()
+        losses.append(loss.detach())
+    allreduce_gradients(params, group)
+    return losses

@@ -7,6 +7,7 @@
 
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
 
 namespace bags {
 
@@ -17,6 +18,50 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- measurement hooks -------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::vector<ProfRec> g_prof_open;
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void prof_begin(int stage, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r;
+    r.stage = stage;
+    r.a = prof_event();
+    r.b = prof_event();
+    cudaEventRecord(r.a, st);
+    g_prof_open.push_back(r);
+}
+
+void prof_end(int stage, cudaStream_t st) {
+    if (!g_prof_on) return;
+    for (size_t i = g_prof_open.size(); i-- > 0;) {
+        if (g_prof_open[i].stage == stage) {
+            ProfRec r = g_prof_open[i];
+            g_prof_open.erase(g_prof_open.begin() + i);
+            cudaEventRecord(r.b, st);
+            g_prof_recs.push_back(r);
+            return;
+        }
+    }
 }
 
 // ---- state layouts -----------------------------------------------------------------------------------------------
@@ -163,6 +208,26 @@ int launch_unpack(int P, int R, int W, int H, const GeomState& g, const BinningS
 using namespace bags;
 
 extern "C" const char* bags_last_error(void) { return g_err; }
+extern "C" unsigned long long bags_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" int bags_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+extern "C" int bags_profile_read(double* ms, unsigned long long* calls) {
+    for (auto& r : g_prof_recs) {
+        BAGS_CUDA_OK(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        BAGS_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        if (r.stage >= 0 && r.stage < BAGS_STAGE_COUNT) {
+            if (ms) ms[r.stage] += t;
+            if (calls) calls[r.stage] += 1;
+        }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    return 0;
+}
 extern "C" int bags_version(void) { return 100; }
 
 extern "C" size_t bags_geom_bytes(int P) { return GeomState::bytes(P < 0 ? 0 : P); }
@@ -238,7 +303,10 @@ extern "C" int bags_rasterize_forward(
 
     // counters + emit chained-scan words are contiguous: one memset
     BAGS_CUDA_OK(cudaMemsetAsync(g.counters, 0, (char*)g.sort.ghist - (char*)g.counters, st));
-    rc = launch_preprocess_fwd(a, g, radii, mean2Dx, mean2Dy, st);
+    {
+        ProfScope ps(BAGS_STAGE_PREPROCESS, st);
+        rc = launch_preprocess_fwd(a, g, radii, mean2Dx, mean2Dy, st);
+    }
     if (rc) return rc;
 
     // num_rendered travels to the host while the depth sort runs
@@ -246,7 +314,11 @@ extern "C" int bags_rasterize_forward(
     BAGS_CUDA_OK(cudaEventRecord(ctx->ev, st));
 
     u32 *sorted_keys, *sorted_idx;
-    rc = launch_sort_pairs(P, g.key_a, g.idx_a, g.key_b, g.idx_b, 0, 32, g.sort, true, st, &sorted_keys, &sorted_idx);
+    {
+        ProfScope ps(BAGS_STAGE_DEPTH_SORT, st);
+        rc = launch_sort_pairs(P, g.key_a, g.idx_a, g.key_b, g.idx_b, 0, 32, g.sort, true, st, &sorted_keys,
+                               &sorted_idx);
+    }
     if (rc) return rc;
 
     BAGS_CUDA_OK(cudaEventSynchronize(ctx->ev));
@@ -267,20 +339,32 @@ extern "C" int bags_rasterize_forward(
     BinningState b = BinningState::from(bin_ptr, R, npass);
 
     if (R > 0) {
-        rc = launch_emit(P, g, sorted_idx, b, tiles_x(width), st);
+        {
+            ProfScope ps(BAGS_STAGE_EMIT, st);
+            rc = launch_emit(P, g, sorted_idx, b, tiles_x(width), st);
+        }
         if (rc) return rc;
         u32 *fk, *fv;
-        rc = launch_sort_pairs(R, b.tile_buf[0], b.id_buf[0], b.tile_buf[1], b.id_buf[1], 0, tile_sort_bits(ntiles),
-                               b.sort, false, st, &fk, &fv);
+        {
+            ProfScope ps(BAGS_STAGE_TILE_SORT, st);
+            rc = launch_sort_pairs(R, b.tile_buf[0], b.id_buf[0], b.tile_buf[1], b.id_buf[1], 0,
+                                   tile_sort_bits(ntiles), b.sort, false, st, &fk, &fv);
+        }
         if (rc) return rc;
         if (fv != b.point_list || fk != b.tile_sorted) {
             set_error("internal: tile sort ping-pong parity mismatch");
             return BAGS_E_INVALID;
         }
     }
-    rc = launch_ranges(R, ntiles, b.tile_sorted, img.ranges, st);
+    {
+        ProfScope ps(BAGS_STAGE_RANGES, st);
+        rc = launch_ranges(R, ntiles, b.tile_sorted, img.ranges, st);
+    }
     if (rc) return rc;
-    rc = launch_blend_fwd(width, height, g, b, img, background, out_color, out_depth, out_alpha, st);
+    {
+        ProfScope ps(BAGS_STAGE_BLEND_FWD, st);
+        rc = launch_blend_fwd(width, height, g, b, img, background, out_color, out_depth, out_alpha, st);
+    }
     if (rc) return rc;
     if (debug) BAGS_CUDA_OK(cudaStreamSynchronize(st));
     return R;
@@ -304,7 +388,9 @@ extern "C" int bags_rasterize_backward(
     char* sp = (char*)align_up((size_t)scratch);
     float* gacc = (float*)sp;
     float* pose_acc = (float*)(sp + align_up((size_t)P * GACC_STRIDE * sizeof(float)));
+    prof_begin(BAGS_STAGE_BWD_CLEAR, st);
     BAGS_CUDA_OK(cudaMemsetAsync(sp, 0, align_up((size_t)P * GACC_STRIDE * sizeof(float)) + 256, st));
+    prof_end(BAGS_STAGE_BWD_CLEAR, st);
 
     BwdOut o;
     o.dL_dmean2D = dL_dmean2D; o.dL_dmean2D_densify = dL_dmean2D_densify; o.covariance = covariance;
@@ -339,12 +425,20 @@ extern "C" int bags_rasterize_backward(
         BinningState b = BinningState::from(const_cast<char*>(binning_buffer), R, tile_sort_passes(ntiles));
         ImageState img = ImageState::from(const_cast<char*>(image_buffer), width, height);
         if (R > 0) {
-            int rc = launch_blend_bwd(width, height, g, b, img, background, dL_dpix, dL_dpix_depth, dL_dalpha, gacc,
+            int rc;
+            {
+                ProfScope ps(BAGS_STAGE_BLEND_BWD, st);
+                rc = launch_blend_bwd(width, height, g, b, img, background, dL_dpix, dL_dpix_depth, dL_dalpha, gacc,
                                       st);
+            }
             if (rc) return rc;
         }
     }
-    int rc = launch_preprocess_bwd(a, g, gacc, pose_acc, o, st);
+    int rc;
+    {
+        ProfScope ps(BAGS_STAGE_PREPROCESS_BWD, st);
+        rc = launch_preprocess_bwd(a, g, gacc, pose_acc, o, st);
+    }
     if (rc) return rc;
     if (debug) BAGS_CUDA_OK(cudaStreamSynchronize(st));
     return 0;

@@ -17,6 +17,14 @@ constexpr int TILE_PIX = TILE_X * TILE_Y;
 
 // ---- error plumbing --------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+void count_launch();
+void prof_begin(int stage, cudaStream_t st);
+void prof_end(int stage, cudaStream_t st);
+struct ProfScope {
+    int stage; cudaStream_t st;
+    ProfScope(int s, cudaStream_t t) : stage(s), st(t) { prof_begin(s, t); }
+    ~ProfScope() { prof_end(stage, st); }
+};
 #define BAGS_CUDA_OK(expr)                                                                       \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
@@ -34,6 +42,7 @@ void set_error(const char* fmt, ...);
                             cudaGetErrorString(_e));                                             \
             return BAGS_E_CUDA;                                                                  \
         }                                                                                        \
+        bags::count_launch();                                                                    \
     } while (0)
 
 // ---- opaque state layouts --------------------------------------------------------------------------------------

@@ -165,6 +165,20 @@ size_t bags_sort_scratch_bytes(int n);
 int bags_sort_pairs_u32(int n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                         int begin_bit, int end_bit, char* scratch, void* stream);
 
+/* ---- measurement hooks (no reference counterpart; used by bench.py) --------------------------------------------
+ * bags_launch_count: number of kernels this library has launched in this process (all devices, all streams).
+ * bags_profile_enable(1): from now on every pipeline stage is bracketed by CUDA events on the launching stream.
+ * bags_profile_read: synchronises the recorded events, ADDS per-stage elapsed milliseconds into ms[BAGS_STAGE_COUNT]
+ * and per-stage launch counts into calls[BAGS_STAGE_COUNT] (either may be NULL), then clears the recordings. */
+enum {
+    BAGS_STAGE_PREPROCESS = 0, BAGS_STAGE_DEPTH_SORT = 1, BAGS_STAGE_EMIT = 2, BAGS_STAGE_TILE_SORT = 3,
+    BAGS_STAGE_RANGES = 4, BAGS_STAGE_BLEND_FWD = 5, BAGS_STAGE_BWD_CLEAR = 6, BAGS_STAGE_BLEND_BWD = 7,
+    BAGS_STAGE_PREPROCESS_BWD = 8, BAGS_STAGE_COUNT = 9
+};
+unsigned long long bags_launch_count(void);
+int bags_profile_enable(int on);
+int bags_profile_read(double* ms, unsigned long long* calls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference interface: names, argument validation and error behaviour (no GPU needed)."""
+import inspect
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from parity_common import PKG, ROOT, load_ours, ref_available, load_ref
+
+import bags_synth as S
+
+
+def test_settings_fields_match_reference_layout():
+    m = load_ours()
+    assert m.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "intrinsic", "sh_degree", "campos", "prefiltered", "debug", "debug_iter")
+
+
+def test_public_surface():
+    m = load_ours()
+    for name in ("GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "compute_relocation"):
+        assert hasattr(m, name)
+    for name in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible", "compute_relocation"):
+        assert hasattr(m._C, name)
+    sig = inspect.signature(m.GaussianRasterizer.forward)
+    assert list(sig.parameters)[1:] == ["means3D", "means2D", "means2D_densify", "shift_factors", "opacities", "shs",
+                                        "colors_precomp", "scales", "rotations", "cov3D_precomp"]
+    from simple_knn._C import distCUDA2  # noqa: F401
+
+
+@pytest.mark.skipif(not ref_available(), reason="reference build (oracle/_ref) not present")
+def test_signatures_equal_reference():
+    ours, ref = load_ours(), load_ref()
+    assert ours.GaussianRasterizationSettings._fields == ref.GaussianRasterizationSettings._fields
+    for fn in ("forward", "markVisible"):
+        assert list(inspect.signature(getattr(ours.GaussianRasterizer, fn)).parameters) == \
+            list(inspect.signature(getattr(ref.GaussianRasterizer, fn)).parameters)
+    assert list(inspect.signature(ours.rasterize_gaussians).parameters) == \
+        list(inspect.signature(ref.rasterize_gaussians).parameters)
+    assert list(inspect.signature(ours.compute_relocation).parameters) == \
+        list(inspect.signature(ref.compute_relocation).parameters)
+
+
+def _settings(m):
+    cam = S.make_camera(32, 32)
+    return m.GaussianRasterizationSettings(
+        image_height=32, image_width=32, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3),
+        scale_modifier=1.0, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, intrinsic=cam.intrinsic,
+        sh_degree=0, campos=cam.campos, prefiltered=False, debug=False, debug_iter=0)
+
+
+def test_exactly_one_of_sh_or_colors():
+    m = load_ours()
+    r = m.GaussianRasterizer(_settings(m))
+    z = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(z, z, z, torch.zeros(3), torch.zeros(4, 1), shs=None, colors_precomp=None, scales=z, rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(z, z, z, torch.zeros(3), torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), colors_precomp=z, scales=z,
+          rotations=torch.zeros(4, 4))
+
+
+def test_exactly_one_of_scale_rot_or_cov():
+    m = load_ours()
+    r = m.GaussianRasterizer(_settings(m))
+    z = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(z, z, z, torch.zeros(3), torch.zeros(4, 1), colors_precomp=z)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(z, z, z, torch.zeros(3), torch.zeros(4, 1), colors_precomp=z, scales=z, rotations=torch.zeros(4, 4),
+          cov3D_precomp=torch.zeros(4, 6))
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    """There is no CPU path: CPU inputs must raise, never fall back."""
+    m = load_ours()
+    r = m.GaussianRasterizer(_settings(m))
+    z = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r(z, z, z, torch.zeros(3), torch.zeros(4, 1), colors_precomp=z, scales=z, rotations=torch.zeros(4, 4))
+    from simple_knn._C import distCUDA2
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        distCUDA2(torch.zeros(10, 3))
+
+
+def test_bad_means_shape():
+    m = load_ours()
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        m._C.rasterize_gaussians(torch.zeros(3), torch.zeros(4, 2), torch.zeros(3), torch.zeros(0), torch.zeros(4, 1),
+                                 torch.zeros(4, 3), torch.zeros(4, 4), 1.0, torch.zeros(0), torch.eye(4), torch.eye(4),
+                                 torch.eye(4), 1.0, 1.0, 8, 8, torch.zeros(4, 16, 3), 0, torch.zeros(3), False, False)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must not route through the oracle or the reference build."""
+    bad = []
+    for dirpath, _, files in os.walk(PKG):
+        if "build" in dirpath.split(os.sep)[-1:]:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                if "raster_oracle" in text or "oracle/_ref" in text or "import oracle" in text or "from oracle" in text:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+def test_synthetic_scene_is_deterministic():
+    cam = S.make_camera(64, 48, seed=100)
+    a = S.make_gaussians(500, cam, seed=0)
+    b = S.make_gaussians(500, cam, seed=0)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    # camera conventions: campos == inverse(view)[3,:3]; projmatrix = view @ P^T
+    inv = torch.linalg.inv(cam.viewmatrix.double())
+    assert torch.allclose(inv[3, :3].float(), cam.campos, atol=1e-6)
+    V, R = S.estimate_tile_instances(a, cam)
+    assert 0 < V <= 500 and R >= V

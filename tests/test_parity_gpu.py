@@ -1,0 +1,303 @@
+"""GPU parity tests (run on the B200 box: python -m pytest tests -m gpu).  Every call goes through the public Python
+API -> ctypes -> C ABI (libbags_b200.so).  Comparisons:
+  * against the golden vectors of the unmodified reference (tests/golden, no reference build needed),
+  * against the live reference build (oracle/_ref) on more and larger scenes,
+  * against the float64 oracle,
+  * size-independent properties at BASELINE.json's full size (1M Gaussians, 1080p).
+Bars: integer / index outputs bit-exact; image, depth, alpha max-abs <= 1e-5; gradients <= 1e-4 relative L2."""
+import ctypes
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import parity_common as pc
+from parity_common import ROOT, rel_l2
+
+sys.path.insert(0, ROOT)
+from oracle import make_golden as MG  # noqa: E402
+from oracle import raster_oracle as O  # noqa: E402
+
+S = pc.S
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+IMG_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_native_library_is_the_one_running():
+    import bags_capi
+    L = bags_capi.lib()
+    n0 = L.bags_launch_count()
+    cam = S.make_camera(64, 48)
+    gs = S.make_gaussians(500, cam, scale=0.05)
+    pc.run_view(pc.load_ours(), cam, gs, S.make_upstream(48, 64), dev())
+    assert L.bags_launch_count() - n0 >= 10          # our kernels were launched, not a fallback
+    with open("/proc/self/maps") as f:
+        assert "libbags_b200.so" in f.read()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(g)[:-4] for g in GOLDEN])
+def test_against_reference_golden(path):
+    name = os.path.basename(path)[:-4]
+    gold = np.load(path)
+    cam, gs, up, kw = MG.build_case(MG.CASES[name])
+    o = pc.run_view(pc.load_ours(), cam, gs, up, dev(), **kw)
+    st = o["state"]
+    # integer / index state: bit-exact
+    assert o["num_rendered"] == int(gold["num_rendered"])
+    assert np.array_equal(o["radii"].numpy(), gold["radii"])
+    assert np.array_equal(st["tiles_touched"].numpy(), gold["state_tiles_touched"])
+    assert np.array_equal(st["point_list"].numpy(), gold["state_point_list"])
+    assert np.array_equal(st["point_list_keys"].numpy(), gold["state_point_list_keys"])
+    assert np.array_equal(st["ranges"].numpy(), gold["state_ranges"])
+    assert np.array_equal(st["n_contrib"].numpy(), gold["state_n_contrib"])
+    # floats
+    for k in ("color", "depth", "weights", "mean2D"):
+        assert float(np.abs(o[k].numpy() - gold[k]).max()) <= IMG_TOL, k
+    assert float(np.abs(st["final_T"].numpy() - gold["state_final_T"]).max()) <= IMG_TOL
+    for k, g in o["grads"].items():
+        if g is None or k == "viewmatrix":
+            continue
+        ref = torch.from_numpy(gold["grad_" + k])
+        if float(ref.abs().max()) == 0:
+            assert float(g.abs().max()) == 0, k
+        else:
+            assert rel_l2(g, ref) <= GRAD_TOL, (k, rel_l2(g, ref))
+
+
+LIVE_CASES = [
+    dict(name="tiny", P=3000, W=160, H=120, scale=0.02),
+    dict(name="bg_shift", P=20000, W=400, H=304, scale=0.01, bg=(1.0, 1.0, 1.0), shift=(1e-3, -5e-4, 2e-4)),
+    dict(name="ragged_deg2", P=50000, W=648, H=421, scale=0.006, sh_degree=2),
+    dict(name="dense_big_splats", P=4000, W=256, H=256, scale=0.08),
+    dict(name="C1", P=100000, W=800, H=800, scale=0.004),
+    dict(name="mod", P=30000, W=320, H=240, scale=0.01, scale_modifier=1.7, sh_degree=1),
+]
+
+
+def _check_live(o, r):
+    m = pc.compare(o, r, verbose=False)
+    assert m["num_rendered"][0] == m["num_rendered"][1]
+    for k in ("radii_mismatch", "tiles_touched_mismatch", "point_list_mismatch", "keys_mismatch", "ranges_mismatch",
+              "n_contrib_mismatch", "xy_bit_mismatch", "conic_opacity_bit_mismatch"):
+        assert m[k] == 0, (k, m[k])
+    for k in ("color_maxabs", "depth_maxabs", "weights_maxabs", "mean2D_maxabs", "final_T_maxabs", "rgb_maxabs"):
+        assert m[k] <= IMG_TOL, (k, m[k])
+    for k, v in m.items():
+        if k.startswith("grad_"):
+            assert isinstance(v, float) and v <= GRAD_TOL, (k, v)
+    return m
+
+
+@pytest.mark.skipif(not pc.ref_available(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("case", LIVE_CASES, ids=[c["name"] for c in LIVE_CASES])
+def test_against_live_reference(case):
+    cam = S.make_camera(case["W"], case["H"])
+    gs = S.make_gaussians(case["P"], cam, scale=case["scale"])
+    up = S.make_upstream(case["H"], case["W"])
+    kw = dict(sh_degree=case.get("sh_degree", 3), bg=case.get("bg", (0, 0, 0)), shift=case.get("shift", (0, 0, 0)),
+              scale_modifier=case.get("scale_modifier", 1.0))
+    o = pc.run_view(pc.load_ours(), cam, gs, up, dev(), **kw)
+    r = pc.run_view(pc.load_ref(), cam, gs, up, dev(), **kw)
+    _check_live(o, r)
+    # Q13: reference view-matrix gradient is a race; ours must have the same sparsity pattern
+    gv = o["grads"]["viewmatrix"].reshape(16)
+    assert float(gv[[3, 7, 8, 9, 11, 12, 13, 15]].abs().max()) == 0.0
+
+
+@pytest.mark.skipif(not pc.ref_available(), reason="reference build (oracle/_ref) not present")
+def test_precomputed_colors_and_covariance_live():
+    c = MG.CASES["tiny_precomp"]
+    cam, gs, up, kw = MG.build_case(c)
+    o = pc.run_view(pc.load_ours(), cam, gs, up, dev(), **kw)
+    r = pc.run_view(pc.load_ref(), cam, gs, up, dev(), **kw)
+    _check_live(o, r)
+
+
+def test_viewmatrix_gradient_is_an_admissible_row():
+    """Ours picks the highest-index visible Gaussian (deterministic member of the reference's race set)."""
+    cam = S.make_camera(160, 120)
+    gs = S.make_gaussians(3000, cam, scale=0.02)
+    up = S.make_upstream(120, 160)
+    o = pc.run_view(pc.load_ours(), cam, gs, up, dev())
+    sc = O.Scene(gs.means3D, gs.opacities, cam.viewmatrix, cam.projmatrix, cam.campos, cam.W, cam.H, cam.tanfovx,
+                 cam.tanfovy, (0, 0, 0), shs=gs.shs, scales=gs.scales, rotations=gs.rotations,
+                 shift_factors=torch.zeros(3), sh_degree=3)
+    f = O.rasterize_forward(sc)
+    b = O.rasterize_backward(sc, f, *up)
+    gv = o["grads"]["viewmatrix"].reshape(16).double()
+    want = b["dL_dviewmatrix"]
+    assert int(b["viewmatrix_row_ids"][-1]) == int(torch.nonzero(o["radii"] > 0).max())
+    assert rel_l2(gv, want) < 1e-3
+
+
+def test_against_float64_oracle():
+    cam = S.make_camera(200, 136, seed=105)
+    gs = S.make_gaussians(5000, cam, seed=7, scale=0.02)
+    up = S.make_upstream(136, 200, seed=3)
+    shift = (5e-4, 1e-4, -2e-4)
+    o = pc.run_view(pc.load_ours(), cam, gs, up, dev(), bg=(0.3, 0.6, 0.9), shift=shift)
+    sc = O.Scene(gs.means3D, gs.opacities, cam.viewmatrix, cam.projmatrix, cam.campos, cam.W, cam.H, cam.tanfovx,
+                 cam.tanfovy, (0.3, 0.6, 0.9), shs=gs.shs, scales=gs.scales, rotations=gs.rotations,
+                 shift_factors=torch.tensor(shift), sh_degree=3)
+    f = O.rasterize_forward(sc)
+    b = O.rasterize_backward(sc, f, *up)
+    assert int((o["radii"].long() != f["radii"]).sum()) <= 2
+    d = (o["color"].double() - f["color"]).abs()
+    assert float((d > 1e-5).float().mean()) < 1e-3 and float(d.max()) < 5e-3
+    for gk, ok in (("means3D", "dL_dmeans3D"), ("shs", "dL_dsh"), ("opacities", "dL_dopacity"),
+                   ("scales", "dL_dscales"), ("rotations", "dL_drotations"), ("projmatrix", "dL_dprojmatrix"),
+                   ("campos", "dL_dcampos"), ("shift_factors", "dL_dshift")):
+        assert rel_l2(o["grads"][gk], b[ok].reshape(o["grads"][gk].shape)) < 2e-3, gk
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_onesweep_sort_matches_stable_sort():
+    import bags_capi as capi
+    L = capi.lib()
+    d = dev()
+    for n, (b0, b1) in [(0, (0, 32)), (1, (0, 32)), (777, (0, 32)), (8192, (0, 13)), (8193, (0, 32)),
+                        (300001, (0, 32)), (1_000_000, (3, 17)), (3_000_000, (0, 15))]:
+        g = torch.Generator().manual_seed(n + 1)
+        keys = torch.randint(0, 2 ** 31 - 1, (max(n, 1),), generator=g, dtype=torch.int64)[:n]
+        if n > 1000:
+            keys[: n // 2] = keys[: n // 2] & 0x3FF
+        keys = keys.to(torch.int32).to(d)
+        vals = torch.arange(n, dtype=torch.int32, device=d)
+        ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+        scratch = torch.empty(int(L.bags_sort_scratch_bytes(n)), dtype=torch.uint8, device=d)
+        kin, vin = keys.clone(), vals.clone()
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
+        rc = L.bags_sort_pairs_u32(n, p(kin), p(vin), p(ko), p(vo), b0, b1, ctypes.c_void_p(scratch.data_ptr()), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        if n == 0:
+            continue
+        kk = (keys.to(torch.int64) >> b0) & ((1 << (b1 - b0)) - 1)
+        order = torch.sort(kk, stable=True).indices
+        assert torch.equal(vo.to(torch.int64), order)
+        assert torch.equal(ko, keys[order])
+
+
+def test_empty_and_degenerate_inputs():
+    m = pc.load_ours()
+    d = dev()
+    cam = S.make_camera(64, 48)
+    st = m.GaussianRasterizationSettings(48, 64, cam.tanfovx, cam.tanfovy, torch.ones(3, device=d), 1.0,
+                                         cam.viewmatrix.to(d), cam.projmatrix.to(d), cam.intrinsic.to(d), 3,
+                                         cam.campos.to(d), False, False, 0)
+    r = m.GaussianRasterizer(st)
+    # P == 0: zero outputs, no launch (rasterize_points.cu:66-83)
+    z3 = torch.zeros(0, 3, device=d)
+    color, radii, depth, w, m2 = r(z3, z3, z3, torch.zeros(3, device=d), torch.zeros(0, 1, device=d),
+                                   shs=torch.zeros(0, 16, 3, device=d), scales=z3, rotations=torch.zeros(0, 4, device=d))
+    assert color.shape == (3, 48, 64) and float(color.abs().max()) == 0 and radii.numel() == 0
+    # every Gaussian behind the camera: R == 0, image == background
+    gs = S.make_gaussians(100, cam, cull_frac=1.0)
+    o = pc.run_view(m, cam, gs, S.make_upstream(48, 64), d, bg=(0.25, 0.5, 0.75))
+    assert o["num_rendered"] == 0 and int(o["radii"].abs().sum()) == 0
+    assert torch.allclose(o["color"][1], torch.full((48, 64), 0.5))
+    assert float(o["depth"].abs().max()) == 0 and float(o["weights"].abs().max()) == 0
+    for k, g in o["grads"].items():
+        if g is not None:
+            assert float(g.abs().max()) == 0, k
+    # a single Gaussian
+    gs1 = S.make_gaussians(1, cam, cull_frac=0.0, scale=0.05)
+    o1 = pc.run_view(m, cam, gs1, S.make_upstream(48, 64), d)
+    assert o1["num_rendered"] == int(o1["state"]["tiles_touched"].sum())
+
+
+def test_mark_visible_and_relocation():
+    m = pc.load_ours()
+    d = dev()
+    cam = S.make_camera(64, 48)
+    gs = S.make_gaussians(5000, cam)
+    st = m.GaussianRasterizationSettings(48, 64, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=d), 1.0,
+                                         cam.viewmatrix.to(d), cam.projmatrix.to(d), cam.intrinsic.to(d), 3,
+                                         cam.campos.to(d), False, False, 0)
+    vis = m.GaussianRasterizer(st).markVisible(gs.means3D.to(d)).cpu()
+    vm = cam.viewmatrix
+    z = gs.means3D @ vm[:3, 2] + vm[3, 2]
+    safe = (z - 0.2).abs() > 1e-5
+    assert torch.equal(vis[safe], (z > 0.2)[safe])
+    # relocation, Eq. (9): against a float64 evaluation of the same formula
+    n_max = 51
+    import math
+    binoms = torch.tensor([[math.comb(n, k) if k <= n else 0 for k in range(n_max)] for n in range(n_max)],
+                          dtype=torch.float32)
+    g = torch.Generator().manual_seed(0)
+    op = torch.rand(200, generator=g) * 0.9 + 0.05
+    sc = torch.rand(200, 3, generator=g)
+    N = torch.randint(1, 8, (200,), generator=g)
+    no, ns = m.compute_relocation(op.to(d), sc.to(d), N.to(d), binoms.to(d), n_max)
+    want_o = 1 - (1 - op.double()) ** (1.0 / N.double())
+    assert torch.allclose(no.cpu().double(), want_o, atol=1e-6)
+    den = torch.zeros(200, dtype=torch.float64)
+    for i in range(200):
+        s = 0.0
+        for a in range(1, int(N[i]) + 1):
+            for k in range(a):
+                s += math.comb(a - 1, k) * ((-1) ** k / math.sqrt(k + 1)) * float(want_o[i]) ** (k + 1)
+        den[i] = s
+    want_s = (op.double() / den)[:, None] * sc.double()
+    assert torch.allclose(ns.cpu().double().reshape(200, 3), want_s, rtol=1e-4, atol=1e-6)
+    if pc.ref_available():
+        ro, rs = pc.load_ref().compute_relocation(op.to(d), sc.to(d), N.to(d), binoms.to(d), n_max)
+        assert torch.allclose(no, ro, rtol=1e-5, atol=1e-7) and torch.allclose(ns, rs, rtol=1e-4, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_full_size_properties_c3():
+    """Size-independent invariants at 1M Gaussians / 1080p (BASELINE.json config 3 shape)."""
+    c = S.CONFIGS["C3"]
+    cam = S.make_camera(c["W"], c["H"])
+    gs = S.make_gaussians(c["P"], cam, scale=0.004)
+    up = S.make_upstream(c["H"], c["W"])
+    m = pc.load_ours()
+    o = pc.run_view(m, cam, gs, up, dev())
+    st = o["state"]
+    R = o["num_rendered"]
+    assert R == int(st["tiles_touched"].sum())
+    assert torch.equal(st["tiles_touched"] > 0, o["radii"] > 0)
+    keys = st["point_list_keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())                      # sortedness
+    tiles = keys >> 32
+    rg = st["ranges"]
+    lens = rg[:, 1] - rg[:, 0]
+    assert int(lens.sum()) == R
+    cnt = torch.bincount(tiles, minlength=rg.shape[0])
+    assert torch.equal(cnt, lens)                                    # ranges partition the sorted list by tile
+    nz = lens > 0
+    assert torch.equal(rg[nz, 0], (torch.cumsum(lens, 0) - lens)[nz])
+    # ties inside a tile keep ascending Gaussian id (stability)
+    same = keys[1:] == keys[:-1]
+    pl = st["point_list"]
+    assert bool((pl[1:][same] > pl[:-1][same]).all())
+    # n_contrib never exceeds the tile's list length
+    W, H = c["W"], c["H"]
+    gx = (W + 15) // 16
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    tile_of_pix = ((ys // 16) * gx + xs // 16).reshape(-1)
+    assert bool((st["n_contrib"] <= lens[tile_of_pix]).all())
+    assert bool(((st["final_T"] >= 0) & (st["final_T"] <= 1)).all())
+    # forward is deterministic bit for bit
+    o2 = pc.run_view(m, cam, gs, up, dev(), backward=False)
+    assert torch.equal(o["color"], o2["color"]) and torch.equal(st["point_list"], o2["state"]["point_list"])
+    # backward is linear in the upstream gradients
+    up2 = [2.0 * u for u in up]
+    o3 = pc.run_view(m, cam, gs, up2, dev())
+    for k in ("means3D", "shs", "opacities", "scales", "rotations", "projmatrix", "campos"):
+        assert rel_l2(o3["grads"][k], 2.0 * o["grads"][k]) < 1e-4, k
+    # culled Gaussians get exactly zero gradients
+    culled = o["radii"] == 0
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        assert float(o["grads"][k][culled].abs().max()) == 0.0, k
