@@ -387,7 +387,7 @@ extern "C" int bags_rasterize_backward(
 
     char* sp = (char*)align_up((size_t)scratch);
     float* gacc = (float*)sp;
-    float* pose_acc = (float*)(sp + align_up((size_t)P * GACC_STRIDE * sizeof(float)));
+    double* pose_acc = (double*)(sp + align_up((size_t)P * GACC_STRIDE * sizeof(float)));
     prof_begin(BAGS_STAGE_BWD_CLEAR, st);
     BAGS_CUDA_OK(cudaMemsetAsync(sp, 0, align_up((size_t)P * GACC_STRIDE * sizeof(float)) + 256, st));
     prof_end(BAGS_STAGE_BWD_CLEAR, st);

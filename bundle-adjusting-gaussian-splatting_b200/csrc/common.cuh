@@ -205,8 +205,8 @@ struct BwdOut {
     float* dL_dcampos;
     float* dL_dshift;
 };
-// gacc: [P][16] accumulated by blend_bwd; pose_acc: [64] floats + counters, zeroed by the caller.
-int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, float* pose_acc,
+// gacc: [P][16] accumulated by blend_bwd; pose_acc: [32] doubles (sums + winner), zeroed by the caller.
+int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, double* pose_acc,
                           const BwdOut& o, cudaStream_t st);
 
 constexpr int GACC_STRIDE = 16;

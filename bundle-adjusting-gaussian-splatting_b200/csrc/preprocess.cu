@@ -18,7 +18,29 @@
 
 namespace bags {
 
-constexpr int PRE_THREADS = 256;
+constexpr int PRE_THREADS = 128;
+constexpr int PRE_WARPS = PRE_THREADS / 32;
+
+// Row stride (floats) of the per-warp SH staging tile: odd => lane-per-row reads are bank-conflict free.
+__host__ __device__ inline int sh_stride(int M) { return (3 * M) | 1; }
+
+// Coalesced load of the SH rows selected by `mask` (one row per Gaussian of the warp) into the warp's tile.
+template <int VEC>
+__device__ __forceinline__ void sh_tile_load(float* tile, int stride, const float* gptr, int row_len, int rows,
+                                             u32 mask, int lane) {
+    const int total = rows * row_len;
+    for (int f = lane * VEC; f < total; f += 32 * VEC) {
+        const int row = f / row_len;
+        if (!((mask >> row) & 1u)) continue;
+        float* t = tile + row * stride + (f - row * row_len);
+        if (VEC == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gptr + f));
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        } else {
+            t[0] = __ldg(gptr + f);
+        }
+    }
+}
 
 struct CamConst {
     float view[16];
@@ -38,7 +60,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                       float focal_x, float focal_y, int grid_x, int grid_y, int prefiltered,
                       int* __restrict__ radii, float* __restrict__ mean2Dx, float* __restrict__ mean2Dy,
                       float4* __restrict__ rec, u32* __restrict__ depth_key, ushort4* __restrict__ rect_out,
-                      unsigned long long* __restrict__ total_tiles) {
+                      unsigned long long* __restrict__ total_tiles, int sh_vec4) {
+    extern __shared__ float sh_tiles[];      // [PRE_WARPS][32][sh_stride(M)], only used when HAS_SH
     __shared__ CamConst cam;
     __shared__ float c2w[4][4];
     __shared__ u32 warp_sums[PRE_THREADS / 32];
@@ -55,17 +78,25 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     __syncthreads();
 
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 my_tiles = 0;
 
-    if (idx < P) {
-        int out_radius = 0;
-        float out_mx = 0.f, out_my = 0.f;
-        u32 out_key = 0xFFFFFFFFu;
-        ushort4 out_rect = make_ushort4(0, 0, 0, 0);
+    // ---- phase 1: geometry (one Gaussian per thread) ---------------------------------------------------------------
+    int out_radius = 0;
+    float out_mx = 0.f, out_my = 0.f;
+    u32 out_key = 0xFFFFFFFFu;
+    ushort4 out_rect = make_ushort4(0, 0, 0, 0);
+    bool emit = false;                  // survives every cull -> gets a record and a colour
+    float pupil_shift = 0.f;
+    float3 p_orig = {0.f, 0.f, 0.f};
+    float2 point_image = {0.f, 0.f};
+    float3 conic = {0.f, 0.f, 0.f};
+    float depth_z = 0.f;
+    const float* vm = cam.view;
+    const float* pm = cam.proj;
 
-        const float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
-        const float* vm = cam.view;
-        const float* pm = cam.proj;
+    if (idx < P) {
+        p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
         const float3 p_view = xform4x3(p_orig, vm);
 
         // Near-plane culling only (auxiliary.h:154).
@@ -86,7 +117,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
             float theta3 = theta2 * theta;
             float theta5 = theta2 * theta3;
             float theta7 = theta2 * theta5;
-            float pupil_shift = cam.shift[0] * theta3 + cam.shift[1] * theta5 + cam.shift[2] * theta7;
+            pupil_shift = cam.shift[0] * theta3 + cam.shift[1] * theta5 + cam.shift[2] * theta7;
             p_hom.w += pupil_shift;
 
             float p_w = 1.0f / (p_hom.w + 0.0000001f);
@@ -126,83 +157,27 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
             float det = (cov_x * cov_z - cov_y * cov_y);
             if (det != 0.0f) {
                 float det_inv = 1.f / det;
-                float3 conic = {cov_z * det_inv, -cov_y * det_inv, cov_x * det_inv};
+                conic = {cov_z * det_inv, -cov_y * det_inv, cov_x * det_inv};
 
                 float mid = 0.5f * (cov_x + cov_z);
                 float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
                 float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
                 float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
-                float2 point_image = {ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H)};
+                point_image = {ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H)};
 
                 uint2 rmin, rmax;
                 tile_rect(point_image.x, point_image.y, (int)my_radius, grid_x, grid_y, rmin, rmax);
                 u32 area = (rmax.x - rmin.x) * (rmax.y - rmin.y);
                 if (area != 0) {
-                    float3 rgb;
-                    u32 clamp_mask = 0;
-                    if (HAS_SH) {
-                        // forward.cu:20-96: direction from the pupil-shifted camera-space point mapped back to world.
-                        float pc0 = vm[0] * p_orig.x + vm[4] * p_orig.y + vm[8] * p_orig.z + vm[12] * 1.0f;
-                        float pc1 = vm[1] * p_orig.x + vm[5] * p_orig.y + vm[9] * p_orig.z + vm[13] * 1.0f;
-                        float pc2 = vm[2] * p_orig.x + vm[6] * p_orig.y + vm[10] * p_orig.z + vm[14] * 1.0f;
-                        float pc3 = vm[3] * p_orig.x + vm[7] * p_orig.y + vm[11] * p_orig.z + vm[15] * 1.0f;
-                        pc2 += pupil_shift;
-                        float3 pos;
-                        pos.x = c2w[0][0] * pc0 + c2w[0][1] * pc1 + c2w[0][2] * pc2 + c2w[0][3] * pc3;
-                        pos.y = c2w[1][0] * pc0 + c2w[1][1] * pc1 + c2w[1][2] * pc2 + c2w[1][3] * pc3;
-                        pos.z = c2w[2][0] * pc0 + c2w[2][1] * pc1 + c2w[2][2] * pc2 + c2w[2][3] * pc3;
-                        float3 dir = {pos.x - cam.campos[0], pos.y - cam.campos[1], pos.z - cam.campos[2]};
-                        float len = sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-                        dir.x = dir.x / len;
-                        dir.y = dir.y / len;
-                        dir.z = dir.z / len;
-
-                        const float* sh = shs + (size_t)idx * M * 3;
-                        float res[3];
-                        const float x = dir.x, y = dir.y, z = dir.z;
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++) {
-                            float r = BAGS_SH_C0 * sh[ch];
-                            if (D > 0) {
-                                r = r - BAGS_SH_C1 * y * sh[3 + ch] + BAGS_SH_C1 * z * sh[6 + ch] -
-                                    BAGS_SH_C1 * x * sh[9 + ch];
-                                if (D > 1) {
-                                    float xx = x * x, yy = y * y, zz = z * z;
-                                    float xy = x * y, yz = y * z, xz = x * z;
-                                    r = r + BAGS_SH_C2_0 * xy * sh[12 + ch] + BAGS_SH_C2_1 * yz * sh[15 + ch] +
-                                        BAGS_SH_C2_2 * (2.0f * zz - xx - yy) * sh[18 + ch] +
-                                        BAGS_SH_C2_3 * xz * sh[21 + ch] + BAGS_SH_C2_4 * (xx - yy) * sh[24 + ch];
-                                    if (D > 2) {
-                                        r = r + BAGS_SH_C3_0 * y * (3.0f * xx - yy) * sh[27 + ch] +
-                                            BAGS_SH_C3_1 * xy * z * sh[30 + ch] +
-                                            BAGS_SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[33 + ch] +
-                                            BAGS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + ch] +
-                                            BAGS_SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[39 + ch] +
-                                            BAGS_SH_C3_5 * z * (xx - yy) * sh[42 + ch] +
-                                            BAGS_SH_C3_6 * x * (xx - 3.0f * yy) * sh[45 + ch];
-                                    }
-                                }
-                            }
-                            r += 0.5f;
-                            if (r < 0) clamp_mask |= (1u << ch);
-                            res[ch] = max(r, 0.0f);
-                        }
-                        rgb = {res[0], res[1], res[2]};
-                    } else {
-                        rgb = {colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]};
-                    }
-
+                    emit = true;
                     out_radius = (int)my_radius;
                     out_mx = p_hom.z;
                     out_my = p_hom.w;
+                    depth_z = p_view.z;
                     out_key = __float_as_uint(p_view.z);
                     out_rect = make_ushort4((unsigned short)rmin.x, (unsigned short)rmin.y,
                                             (unsigned short)(rmax.x - rmin.x), (unsigned short)(rmax.y - rmin.y));
                     my_tiles = area;
-                    rec[3 * (size_t)idx + 0] =
-                        make_float4(point_image.x, point_image.y, p_view.z, __uint_as_float(clamp_mask));
-                    rec[3 * (size_t)idx + 1] = make_float4(conic.x, conic.y, conic.z, opacities[idx]);
-                    rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
                 }
             }
         }
@@ -211,6 +186,79 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         mean2Dy[idx] = out_my;
         depth_key[idx] = out_key;
         rect_out[idx] = out_rect;
+    }
+
+    // ---- phase 2: colour.  SH rows of the surviving Gaussians are staged per warp with coalesced 128-bit loads ------
+    float3 rgb = {0.f, 0.f, 0.f};
+    u32 clamp_mask = 0;
+    if (HAS_SH) {
+        const int row_len = 3 * M;
+        const int stride = sh_stride(M);
+        float* tile = sh_tiles + (size_t)warp * 32 * stride;
+        const int warp_first = blockIdx.x * PRE_THREADS + warp * 32;
+        const int rows = min(32, P - warp_first);
+        const u32 need = __ballot_sync(0xffffffffu, emit);
+        if (need != 0 && rows > 0) {
+            const float* gsh = shs + (size_t)warp_first * row_len;
+            if (sh_vec4) sh_tile_load<4>(tile, stride, gsh, row_len, rows, need, lane);
+            else sh_tile_load<1>(tile, stride, gsh, row_len, rows, need, lane);
+        }
+        __syncwarp();
+        if (emit) {
+            // forward.cu:20-96: direction from the pupil-shifted camera-space point mapped back to world.
+            float pc0 = vm[0] * p_orig.x + vm[4] * p_orig.y + vm[8] * p_orig.z + vm[12] * 1.0f;
+            float pc1 = vm[1] * p_orig.x + vm[5] * p_orig.y + vm[9] * p_orig.z + vm[13] * 1.0f;
+            float pc2 = vm[2] * p_orig.x + vm[6] * p_orig.y + vm[10] * p_orig.z + vm[14] * 1.0f;
+            float pc3 = vm[3] * p_orig.x + vm[7] * p_orig.y + vm[11] * p_orig.z + vm[15] * 1.0f;
+            pc2 += pupil_shift;
+            float3 pos;
+            pos.x = c2w[0][0] * pc0 + c2w[0][1] * pc1 + c2w[0][2] * pc2 + c2w[0][3] * pc3;
+            pos.y = c2w[1][0] * pc0 + c2w[1][1] * pc1 + c2w[1][2] * pc2 + c2w[1][3] * pc3;
+            pos.z = c2w[2][0] * pc0 + c2w[2][1] * pc1 + c2w[2][2] * pc2 + c2w[2][3] * pc3;
+            float3 dir = {pos.x - cam.campos[0], pos.y - cam.campos[1], pos.z - cam.campos[2]};
+            float len = sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+            dir.x = dir.x / len;
+            dir.y = dir.y / len;
+            dir.z = dir.z / len;
+
+            const float* sh = tile + lane * stride;
+            float res[3];
+            const float x = dir.x, y = dir.y, z = dir.z;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                float r = BAGS_SH_C0 * sh[ch];
+                if (D > 0) {
+                    r = r - BAGS_SH_C1 * y * sh[3 + ch] + BAGS_SH_C1 * z * sh[6 + ch] - BAGS_SH_C1 * x * sh[9 + ch];
+                    if (D > 1) {
+                        float xx = x * x, yy = y * y, zz = z * z;
+                        float xy = x * y, yz = y * z, xz = x * z;
+                        r = r + BAGS_SH_C2_0 * xy * sh[12 + ch] + BAGS_SH_C2_1 * yz * sh[15 + ch] +
+                            BAGS_SH_C2_2 * (2.0f * zz - xx - yy) * sh[18 + ch] + BAGS_SH_C2_3 * xz * sh[21 + ch] +
+                            BAGS_SH_C2_4 * (xx - yy) * sh[24 + ch];
+                        if (D > 2) {
+                            r = r + BAGS_SH_C3_0 * y * (3.0f * xx - yy) * sh[27 + ch] +
+                                BAGS_SH_C3_1 * xy * z * sh[30 + ch] +
+                                BAGS_SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[33 + ch] +
+                                BAGS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + ch] +
+                                BAGS_SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[39 + ch] +
+                                BAGS_SH_C3_5 * z * (xx - yy) * sh[42 + ch] +
+                                BAGS_SH_C3_6 * x * (xx - 3.0f * yy) * sh[45 + ch];
+                        }
+                    }
+                }
+                r += 0.5f;
+                if (r < 0) clamp_mask |= (1u << ch);
+                res[ch] = max(r, 0.0f);
+            }
+            rgb = {res[0], res[1], res[2]};
+        }
+    } else if (emit) {
+        rgb = {colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]};
+    }
+    if (emit) {
+        rec[3 * (size_t)idx + 0] = make_float4(point_image.x, point_image.y, depth_z, __uint_as_float(clamp_mask));
+        rec[3 * (size_t)idx + 1] = make_float4(conic.x, conic.y, conic.z, opacities[idx]);
+        rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
     }
 
     // Block-reduce the tile-instance count; one 64-bit atomic per CTA replaces the reference's InclusiveSum +
@@ -234,19 +282,31 @@ int launch_preprocess_fwd(const FwdArgs& a, GeomState& g, int* radii, float* mea
     const int blocks = (a.P + PRE_THREADS - 1) / PRE_THREADS;
     const bool has_sh = a.colors_precomp == nullptr;
     const bool has_cov = a.cov3D_precomp != nullptr;
+    const size_t smem = has_sh ? (size_t)PRE_WARPS * 32 * sh_stride(a.M) * sizeof(float) : 0;
+    if (smem > 200 * 1024) {
+        set_error("preprocess: %d SH coefficients per Gaussian do not fit the staging tile", a.M);
+        return BAGS_E_INVALID;
+    }
+    if (smem > 48 * 1024) {
+        BAGS_CUDA_OK(cudaFuncSetAttribute(preprocess_fwd_kernel<true, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BAGS_CUDA_OK(cudaFuncSetAttribute(preprocess_fwd_kernel<true, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int vec4 = has_sh && ((3 * a.M) % 4 == 0) && (((size_t)a.shs & 15) == 0);
 #define BAGS_PRE_ARGS                                                                                              \
     a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations, a.opacities, a.shs, a.cov3D_precomp,        \
         a.colors_precomp, a.viewmatrix, a.projmatrix, a.cam_pos, a.shift_factors, a.W, a.H, a.tan_fovx, a.tan_fovy, \
         a.focal_x, a.focal_y, gx, gy, a.prefiltered, radii, mean2Dx, mean2Dy, g.rec, g.key_a, g.rect,           \
-        g.counters
+        g.counters, vec4
     if (has_sh && has_cov)
-        preprocess_fwd_kernel<true, true><<<blocks, PRE_THREADS, 0, st>>>(BAGS_PRE_ARGS);
+        preprocess_fwd_kernel<true, true><<<blocks, PRE_THREADS, smem, st>>>(BAGS_PRE_ARGS);
     else if (has_sh)
-        preprocess_fwd_kernel<true, false><<<blocks, PRE_THREADS, 0, st>>>(BAGS_PRE_ARGS);
+        preprocess_fwd_kernel<true, false><<<blocks, PRE_THREADS, smem, st>>>(BAGS_PRE_ARGS);
     else if (has_cov)
-        preprocess_fwd_kernel<false, true><<<blocks, PRE_THREADS, 0, st>>>(BAGS_PRE_ARGS);
+        preprocess_fwd_kernel<false, true><<<blocks, PRE_THREADS, smem, st>>>(BAGS_PRE_ARGS);
     else
-        preprocess_fwd_kernel<false, false><<<blocks, PRE_THREADS, 0, st>>>(BAGS_PRE_ARGS);
+        preprocess_fwd_kernel<false, false><<<blocks, PRE_THREADS, smem, st>>>(BAGS_PRE_ARGS);
 #undef BAGS_PRE_ARGS
     BAGS_LAUNCH_OK("preprocess_fwd_kernel");
     return 0;

@@ -23,10 +23,44 @@
 
 namespace bags {
 
-constexpr int PB_THREADS = 256;
-// pose_acc layout (floats): [0..15] sum dL_dproj, [16..18] sum dL_dcampos, [19..21] sum dL_dshift,
-// [32] (as u32) 1 + highest visible index
-constexpr int PA_PROJ = 0, PA_CAMPOS = 16, PA_SHIFT = 19, PA_WINNER = 32, PA_NRED = 22;
+constexpr int PB_THREADS = 128;
+constexpr int PB_WARPS = PB_THREADS / 32;
+// pose_acc layout (doubles): [0..15] sum dL_dproj, [16..18] sum dL_dcampos, [19..21] sum dL_dshift,
+// [22] (as u32) 1 + highest visible index.  Sums are carried in FP64 from the warp butterfly on: the terms are
+// signed and cancel heavily (condition numbers ~100 on wide-splat scenes), so the summation itself adds no error.
+constexpr int PA_PROJ = 0, PA_CAMPOS = 16, PA_SHIFT = 19, PA_WINNER = 22, PA_NRED = 22;
+
+// Row stride (floats) of the per-warp SH staging tile: odd, so that lane-per-row access is bank-conflict free.
+__host__ __device__ inline int sh_tile_stride(int M) { return (3 * M) | 1; }
+
+// Cooperative, coalesced copy between the per-warp SH tile (32 rows, one per Gaussian of the warp) and the
+// contiguous global block of the same 32 Gaussians.  `rows` = number of valid Gaussians (tail warp), `mask` selects
+// rows (loads only; stores are dense).  VEC = 4 needs 3M % 4 == 0 and a 16-byte aligned base.
+template <int VEC, bool LOAD>
+__device__ __forceinline__ void sh_tile_copy(float* tile, int stride, float* gptr, int row_len, int rows, u32 mask,
+                                             int lane) {
+    const int total = rows * row_len;
+    for (int f = lane * VEC; f < total; f += 32 * VEC) {
+        const int row = f / row_len;
+        const int col = f - row * row_len;
+        float* t = tile + row * stride + col;
+        if (LOAD) {
+            if (!((mask >> row) & 1u)) continue;
+            if (VEC == 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(gptr + f));
+                t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+            } else {
+                t[0] = __ldg(gptr + f);
+            }
+        } else {
+            if (VEC == 4) {
+                *reinterpret_cast<float4*>(gptr + f) = make_float4(t[0], t[1], t[2], t[3]);
+            } else {
+                gptr[f] = t[0];
+            }
+        }
+    }
+}
 
 struct Cov2DBack {
     float dL_dcov[6];
@@ -136,12 +170,13 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                       const float* __restrict__ cov3D_precomp, const float* __restrict__ viewmatrix,
                       const float* __restrict__ projmatrix, const float* __restrict__ campos_ptr, int W, int H,
                       float tan_fovx, float tan_fovy, float focal_x, float focal_y, const float4* __restrict__ rec,
-                      const float* __restrict__ gacc, float* __restrict__ pose_acc, BwdOut o) {
+                      const float* __restrict__ gacc, double* __restrict__ pose_acc, BwdOut o, int sh_vec4) {
+    extern __shared__ float sh_tiles[];           // [PB_WARPS][32][sh_tile_stride(M)]
     __shared__ float view[16];
     __shared__ float proj[16];
     __shared__ float campos[3];
-    __shared__ float s_red[PB_THREADS / 32][PA_NRED];
-    __shared__ u32 s_win[PB_THREADS / 32];
+    __shared__ double s_red[PB_WARPS][PA_NRED];
+    __shared__ u32 s_win[PB_WARPS];
     if (threadIdx.x < 16) {
         view[threadIdx.x] = viewmatrix[threadIdx.x];
         proj[threadIdx.x] = projmatrix[threadIdx.x];
@@ -157,9 +192,25 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     for (int k = 0; k < PA_NRED; k++) pose[k] = 0.f;
     u32 winner = 0;
 
+    // ---- stage the SH rows of this warp's visible Gaussians in shared memory (coalesced 128-bit loads) ----------
+    const int sh_len = 3 * M;
+    const int stride = sh_tile_stride(M);
+    float* tile = sh_tiles + (size_t)warp * 32 * stride;
+    float* my_sh = tile + lane * stride;          // this lane's row: SH in, dL_dSH out (in place)
+    const int warp_first = blockIdx.x * PB_THREADS + warp * 32;
+    const int rows = min(32, P - warp_first);
+    const bool lane_visible = (idx < P) && (radii[idx] > 0);
+    const u32 vis_mask = __ballot_sync(0xffffffffu, lane_visible);
+    if (shs != nullptr && rows > 0) {
+        float* gsh = const_cast<float*>(shs) + (size_t)warp_first * sh_len;
+        if (sh_vec4) sh_tile_copy<4, true>(tile, stride, gsh, sh_len, rows, vis_mask, lane);
+        else sh_tile_copy<1, true>(tile, stride, gsh, sh_len, rows, vis_mask, lane);
+        __syncwarp();
+    }
+
     if (idx < P) {
         const size_t i = (size_t)idx;
-        const bool visible = radii[idx] > 0;
+        const bool visible = lane_visible;
         float out_mean3D[3] = {0.f, 0.f, 0.f};
         float out_mean2D[2] = {0.f, 0.f};
         float out_dens[2] = {0.f, 0.f};
@@ -260,8 +311,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                 const float3 dir_orig = {m.x - campos[0], m.y - campos[1], m.z - campos[2]};
                 const float len = sqrt(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
                 const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-                const float* sh = shs + i * M * 3;
-                float* dsh = o.dL_dsh + i * M * 3;
+                const float* sh = my_sh;
+                float* dsh = my_sh;              // in place: every slot is read before it is overwritten
                 float dRGB[3];
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) dRGB[ch] = dL_dcolor[ch] * ((clamp_mask >> ch) & 1u ? 0 : 1);
@@ -273,22 +324,25 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                 for (int ch = 0; ch < 3; ch++) {
                     const float g = dRGB[ch];
                     float dx = 0.f, dy = 0.f, dz = 0.f;
+                    // read this channel's coefficients first, then overwrite the same slots with their gradients
+                    float c[16];
+#pragma unroll
+                    for (int k = 1; k < 16; k++) c[k] = (k < (D + 1) * (D + 1)) ? sh[k * 3 + ch] : 0.f;
                     dsh[0 * 3 + ch] = BAGS_SH_C0 * g;
                     if (D > 0) {
                         dsh[1 * 3 + ch] = (-BAGS_SH_C1 * y) * g;
                         dsh[2 * 3 + ch] = (BAGS_SH_C1 * z) * g;
                         dsh[3 * 3 + ch] = (-BAGS_SH_C1 * x) * g;
-                        dx = -BAGS_SH_C1 * sh[3 * 3 + ch];
-                        dy = -BAGS_SH_C1 * sh[1 * 3 + ch];
-                        dz = BAGS_SH_C1 * sh[2 * 3 + ch];
+                        dx = -BAGS_SH_C1 * c[3];
+                        dy = -BAGS_SH_C1 * c[1];
+                        dz = BAGS_SH_C1 * c[2];
                         if (D > 1) {
                             dsh[4 * 3 + ch] = (BAGS_SH_C2_0 * xy) * g;
                             dsh[5 * 3 + ch] = (BAGS_SH_C2_1 * yz) * g;
                             dsh[6 * 3 + ch] = (BAGS_SH_C2_2 * (2.f * zz - xx - yy)) * g;
                             dsh[7 * 3 + ch] = (BAGS_SH_C2_3 * xz) * g;
                             dsh[8 * 3 + ch] = (BAGS_SH_C2_4 * (xx - yy)) * g;
-                            const float s4 = sh[4 * 3 + ch], s5 = sh[5 * 3 + ch], s6 = sh[6 * 3 + ch],
-                                        s7 = sh[7 * 3 + ch], s8 = sh[8 * 3 + ch];
+                            const float s4 = c[4], s5 = c[5], s6 = c[6], s7 = c[7], s8 = c[8];
                             dx += BAGS_SH_C2_0 * y * s4 + BAGS_SH_C2_2 * 2.f * -x * s6 + BAGS_SH_C2_3 * z * s7 +
                                   BAGS_SH_C2_4 * 2.f * x * s8;
                             dy += BAGS_SH_C2_0 * x * s4 + BAGS_SH_C2_1 * z * s5 + BAGS_SH_C2_2 * 2.f * -y * s6 +
@@ -302,9 +356,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                                 dsh[13 * 3 + ch] = (BAGS_SH_C3_4 * x * (4.f * zz - xx - yy)) * g;
                                 dsh[14 * 3 + ch] = (BAGS_SH_C3_5 * z * (xx - yy)) * g;
                                 dsh[15 * 3 + ch] = (BAGS_SH_C3_6 * x * (xx - 3.f * yy)) * g;
-                                const float s9 = sh[9 * 3 + ch], s10 = sh[10 * 3 + ch], s11 = sh[11 * 3 + ch],
-                                            s12 = sh[12 * 3 + ch], s13 = sh[13 * 3 + ch], s14 = sh[14 * 3 + ch],
-                                            s15 = sh[15 * 3 + ch];
+                                const float s9 = c[9], s10 = c[10], s11 = c[11], s12 = c[12], s13 = c[13],
+                                            s14 = c[14], s15 = c[15];
                                 dx += (BAGS_SH_C3_0 * s9 * 3.f * 2.f * xy + BAGS_SH_C3_1 * s10 * yz +
                                        BAGS_SH_C3_2 * s11 * -2.f * xy + BAGS_SH_C3_3 * s12 * -3.f * 2.f * xz +
                                        BAGS_SH_C3_4 * s13 * (-3.f * xx + 4.f * zz - yy) +
@@ -392,8 +445,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
             pose[PA_SHIFT + 1] = dshift[1];
             pose[PA_SHIFT + 2] = dshift[2];
         } else if (o.dL_dsh != nullptr && M > 0) {
-            float* dsh = o.dL_dsh + i * M * 3;
-            for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
+            for (int k = 0; k < sh_len; k++) my_sh[k] = 0.f;
         }
 
         // dense outputs, every row
@@ -417,10 +469,18 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         for (int k = 0; k < 4; k++) o.dL_drot[4 * i + k] = out_rot[k];
     }
 
-    // ---- pose terms: warp butterfly -> CTA -> one atomic per term ------------------------------------------------
+    // ---- dL_dSH: the warp's 32 rows leave as one contiguous, fully coalesced block ------------------------------
+    if (o.dL_dsh != nullptr && M > 0 && rows > 0) {
+        __syncwarp();
+        float* gdst = o.dL_dsh + (size_t)warp_first * sh_len;
+        if (sh_vec4) sh_tile_copy<4, false>(tile, stride, gdst, sh_len, rows, 0xffffffffu, lane);
+        else sh_tile_copy<1, false>(tile, stride, gdst, sh_len, rows, 0xffffffffu, lane);
+    }
+
+    // ---- pose terms: FP64 warp butterfly -> CTA -> one atomic per term -------------------------------------------
 #pragma unroll
     for (int k = 0; k < PA_NRED; k++) {
-        float v = pose[k];
+        double v = (double)pose[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0) s_red[warp][k] = v;
@@ -429,16 +489,16 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     if (lane == 0) s_win[warp] = wwin;
     __syncthreads();
     if (threadIdx.x < PA_NRED) {
-        float v = 0.f;
+        double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < PB_THREADS / 32; w++) v += s_red[w][threadIdx.x];
-        if (v != 0.f) atomicAdd(&pose_acc[threadIdx.x], v);
+        for (int w = 0; w < PB_WARPS; w++) v += s_red[w][threadIdx.x];
+        if (v != 0.0) atomicAdd(&pose_acc[threadIdx.x], v);
     }
     if (threadIdx.x == 32) {
         u32 m = 0;
 #pragma unroll
-        for (int w = 0; w < PB_THREADS / 32; w++) m = max(m, s_win[w]);
-        if (m) atomicMax(reinterpret_cast<u32*>(pose_acc) + PA_WINNER, m);
+        for (int w = 0; w < PB_WARPS; w++) m = max(m, s_win[w]);
+        if (m) atomicMax(reinterpret_cast<u32*>(pose_acc + PA_WINNER), m);
     }
 }
 
@@ -447,19 +507,20 @@ __global__ void pose_finalize_kernel(int P, const float* __restrict__ means3D, c
                                      const float* __restrict__ rotations, float scale_modifier,
                                      const float* __restrict__ cov3D_precomp, const float* __restrict__ viewmatrix,
                                      float tan_fovx, float tan_fovy, float focal_x, float focal_y,
-                                     const float* __restrict__ gacc, const float* __restrict__ pose_acc, BwdOut o) {
+                                     const float* __restrict__ gacc, const double* __restrict__ pose_acc, BwdOut o) {
     const int t = threadIdx.x;
     const float invP = (float)P;
-    if (t < 16) o.dL_dprojmatrix[t] = pose_acc[PA_PROJ + t] / invP;
+    // sum rounded to fp32 once, then the reference's fp32 division by P (torch mean)
+    if (t < 16) o.dL_dprojmatrix[t] = (float)pose_acc[PA_PROJ + t] / invP;
     if (t < 3) {
-        o.dL_dcampos[t] = pose_acc[PA_CAMPOS + t] / invP;
-        o.dL_dshift[t] = pose_acc[PA_SHIFT + t] / invP;
+        o.dL_dcampos[t] = (float)pose_acc[PA_CAMPOS + t] / invP;
+        o.dL_dshift[t] = (float)pose_acc[PA_SHIFT + t] / invP;
     }
     if (t == 0) {
         float vm[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) vm[k] = 0.f;
-        const u32 win = reinterpret_cast<const u32*>(pose_acc)[PA_WINNER];
+        const u32 win = *reinterpret_cast<const u32*>(pose_acc + PA_WINNER);
         if (win) {
             const int idx = (int)win - 1;
             const size_t i = (size_t)idx;
@@ -502,13 +563,22 @@ __global__ void pose_finalize_kernel(int P, const float* __restrict__ means3D, c
     }
 }
 
-int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, float* pose_acc, const BwdOut& o,
+int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, double* pose_acc, const BwdOut& o,
                           cudaStream_t st) {
     const int blocks = (a.P + PB_THREADS - 1) / PB_THREADS;
-    preprocess_bwd_kernel<<<blocks, PB_THREADS, 0, st>>>(
+    const size_t smem = (size_t)PB_WARPS * 32 * sh_tile_stride(a.M) * sizeof(float);
+    if (smem > 200 * 1024) {
+        set_error("preprocess_bwd: %d SH coefficients per Gaussian do not fit the staging tile", a.M);
+        return BAGS_E_INVALID;
+    }
+    if (smem > 48 * 1024)
+        BAGS_CUDA_OK(cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    const int vec4 = ((3 * a.M) % 4 == 0) && (((size_t)a.shs & 15) == 0) && (((size_t)o.dL_dsh & 15) == 0);
+    preprocess_bwd_kernel<<<blocks, PB_THREADS, smem, st>>>(
         a.P, a.D, a.M, a.means3D, a.radii, a.shs, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp,
         a.viewmatrix, a.projmatrix, a.campos, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, g.rec, gacc,
-        pose_acc, o);
+        pose_acc, o, vec4);
     BAGS_LAUNCH_OK("preprocess_bwd_kernel");
     pose_finalize_kernel<<<1, 32, 0, st>>>(a.P, a.means3D, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp,
                                            a.viewmatrix, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, gacc,

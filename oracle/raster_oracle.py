@@ -619,6 +619,10 @@ def preprocess_backward(sc, pre, acc):
     out["dL_dcampos"] = dcampos.sum(0) / P                            # Q12: mean over all P rows
     out["dL_dprojmatrix"] = dproj.sum(0) / P
     out["dL_dshift"] = dshift.sum(0) / P
+    # conditioning of the three reduced vectors: mean over P of |term| (fp32 summation order perturbs the reference's
+    # own .mean(0) by ~1e-6 of this, which can exceed 1e-4 of the signed result when the terms cancel)
+    out["pose_abs"] = {"dL_dcampos": dcampos.abs().sum(0) / P, "dL_dprojmatrix": dproj.abs().sum(0) / P,
+                       "dL_dshift": dshift.abs().sum(0) / P}
     out["covariance"] = acc["covariance"].reshape(P, 1) + 1e-4        # Q14
     out["viewmatrix_rows"] = vrow / P                                  # Q13: admissible values (one row each)
     out["viewmatrix_row_ids"] = vi
