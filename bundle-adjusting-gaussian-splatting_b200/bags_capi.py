@@ -52,6 +52,7 @@ SIGNATURES = {
     "bags_launch_count": (ctypes.c_ulonglong, []),
     "bags_profile_enable": (c_int, [c_int]),
     "bags_profile_read": (c_int, [_P, _P]),
+    "bags_set_tuning": (c_int, [c_int, c_int]),
     "bags_sort_scratch_bytes": (c_size_t, [c_int]),
     "bags_sort_pairs_u32": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
 }

@@ -5,30 +5,54 @@
 // T * (1 - alpha) < 1e-4; accumulate colour, depth (sum d * alpha * T) and alpha (sum alpha * T); write final_T and
 // n_contrib for the backward.  Backward restates renderCUDA of backward.cu:925-1129.
 //
-// Differences from the reference are in staging and reduction only:
+// Differences from the reference are in staging, scheduling and reduction only:
 //   * one packed 48-byte record per splat (see preprocess.cu) is gathered into shared memory -- colour and depth
 //     included, where the reference re-reads colour from global memory per pixel (forward.cu:764);
-//   * a warp owns an 8x4 pixel patch and leaves the splat loop as soon as all of its pixels are done
-//     (the reference only stops when the whole 256-pixel CTA is done);
-//   * the backward only walks list positions below the CTA's largest n_contrib, reduces the 12 per-splat gradient
-//     terms across the warp with a transposed butterfly (16 + 3 shuffles instead of 60) and commits them once per
-//     (warp, splat) with three 128-bit vector reductions (red.global.add.v4.f32) into a packed 16-float record --
-//     instead of 13 scalar global atomics per (pixel, splat) pair (backward.cu:1067-1116).  (Shared-memory fp32
-//     atomics are CAS loops on this architecture, so a per-CTA shared accumulation stage was measured and dropped.)
+//   * culling below tile granularity.  The tile is cut into 4x2-pixel cells; while a batch is staged, the loading
+//     thread turns the splat's alpha >= 1/255 bounding box into a 32-bit cell mask.  The tile is split into eight 8x4
+//     patches; a warp owns PPT of them (one pixel per lane and patch, PPT = 1, 2 or 4 pixels per thread), tests 32
+//     candidates at a time against its cells with one ballot and evaluates, per patch, only the splats whose box
+//     reaches that patch.  List order per pixel is untouched, so n_contrib, final_T and every threshold decision are
+//     those of the reference;
+//   * the backward only walks list positions below the largest n_contrib of the CTA / warp / patch.  The 13
+//     per-splat gradient terms of a thread's PPT pixels are added in registers, then reduced across the warp with
+//     ONE transposed butterfly per (warp, splat) (16 shuffles for 32 * PPT pixels) and committed with three 128-bit
+//     vector reductions (red.global.add.v4.f32) + one scalar into a packed 16-float record -- instead of 13 scalar
+//     global atomics per (pixel, splat) pair (backward.cu:1067-1116).  (Shared-memory fp32 atomics are CAS loops on
+//     this architecture, so a per-CTA shared accumulation stage was measured and dropped.)
+//   * the back-to-front recurrences accum = last_alpha * last_colour + (1 - last_alpha) * accum (backward.cu:1060,
+//     1069,1077) are evaluated at the end of the iteration that produces (alpha, colour) instead of at the start of
+//     the next one: same operands, same operations, five fewer live registers per pixel.
 #include "../../include/bags_b200.h"
 #include "common.cuh"
 
 namespace bags {
 
-constexpr int BLEND_THREADS = 256;
 constexpr int BATCH = 256;
+constexpr u32 FULL = 0xffffffffu;
 
-// thread -> pixel inside the 16x16 tile: warp w covers the 8x4 patch at ((w&1)*8, (w>>1)*4)
-__device__ __forceinline__ void thread_pixel(int tid, int& lx, int& ly) {
-    const int w = tid >> 5, l = tid & 31;
-    lx = ((w & 1) << 3) + (l & 7);
-    ly = ((w >> 1) << 2) + (l >> 3);
-}
+// pixels per thread of the two blend kernels (1, 2 or 4); see bags_set_tuning
+static int g_fwd_ppt = 2;
+static int g_bwd_ppt = 2;
+
+// Tile decomposition.  Cell grid: 4 columns of 4 pixels x 8 rows of 2 pixels, bit = row * 4 + column.  Patch (x, y),
+// x in 0..1, y in 0..3, is the 8x4 pixel block at (8x, 4y) = cells {2x, 2x+1} x {2y, 2y+1} = bits 0x33 << (8y + 2x).
+// A CTA has 8 / PPT warps; warp w owns the PPT vertically stacked patches (w & 1, (w >> 1) * PPT + k), k < PPT;
+// lane l is pixel (l & 7, l >> 3) of each of them.
+template <int PPT>
+struct WarpPixels {
+    int x, ybase;
+    __device__ __forceinline__ WarpPixels(int w) : x(w & 1), ybase((w >> 1) * PPT) {}
+    __device__ __forceinline__ int cell_shift(int k) const { return ((ybase + k) << 3) + (x << 1); }
+    __device__ __forceinline__ u32 cells() const {
+        u32 m = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; k++) m |= 0x33u << cell_shift(k);
+        return m;
+    }
+    __device__ __forceinline__ int lx(int lane) const { return (x << 3) + (lane & 7); }
+    __device__ __forceinline__ int ly(int lane, int k) const { return ((ybase + k) << 2) + (lane >> 3); }
+};
 
 // Shared-memory accesses through 32-bit shared-window addresses: one IMAD + LDS.128 per record field instead of
 // the generic-pointer conversion sequence the compiler otherwise re-emits inside the hot loop.
@@ -44,143 +68,185 @@ __device__ __forceinline__ u32 lds32(u32 a) {
     return v;
 }
 
-// Conservative screen-space half extents of the region where a splat can reach alpha >= 1/255:
+// Cells of the tile at (tx0, ty0) that a splat can reach with alpha >= 1/255.
 // o * exp(-0.5 d^T Q d) >= 1/255  <=>  d^T Q d <= 2 ln(255 o) =: 2t, whose bounding box has half widths
 // sqrt(2t * Qinv_xx) = sqrt(2t * c / det), sqrt(2t * a / det).  Inflated by 0.1% + half a pixel so that fp32 rounding
 // of `power` can never make a culled pair pass the reference's alpha test.  o < 1/255 can never contribute
-// (alpha <= o), encoded as a negative extent.  Non-finite / indefinite conics yield NaN extents, which the
-// NaN-safe test below treats as "hit" (never culled).
-__device__ __forceinline__ float2 splat_extent(const float4 con_o) {
+// (alpha <= o): empty mask.  Non-finite / indefinite conics yield NaN extents, which the clamps below turn into
+// "every cell" (never culled).
+__device__ __forceinline__ u32 splat_cellmask(const float4 q0, const float4 con_o, const float tx0, const float ty0) {
     const float t = logf(255.0f * con_o.w);
-    if (t < 0.0f) return make_float2(-1.0f, -1.0f);
+    if (t < 0.0f) return 0u;
     const float det = con_o.x * con_o.z - con_o.y * con_o.y;
     const float k = 2.0f * t / det;
-    return make_float2(sqrtf(k * con_o.z) * 1.001f + 0.5f, sqrtf(k * con_o.x) * 1.001f + 0.5f);
+    const float ex = sqrtf(k * con_o.z) * 1.001f + 0.5f;
+    const float ey = sqrtf(k * con_o.x) * 1.001f + 0.5f;
+    // pixel centres are integers: cell column i holds x in [4i, 4i+3], cell row j holds y in [2j, 2j+1] (tile-local)
+    float lo_x = q0.x - ex - tx0, hi_x = q0.x + ex - tx0;
+    float lo_y = q0.y - ey - ty0, hi_y = q0.y + ey - ty0;
+    lo_x = fminf(fmaxf(lo_x, -8.0f), 32.0f);   // NaN -> -8
+    hi_x = fmaxf(fminf(hi_x, 32.0f), -8.0f);   // NaN -> 32
+    lo_y = fminf(fmaxf(lo_y, -8.0f), 32.0f);
+    hi_y = fmaxf(fminf(hi_y, 32.0f), -8.0f);
+    const int i0 = max(0, (int)ceilf((lo_x - 3.0f) * 0.25f)), i1 = min(3, (int)floorf(hi_x * 0.25f));
+    const int j0 = max(0, (int)ceilf((lo_y - 1.0f) * 0.5f)), j1 = min(7, (int)floorf(hi_y * 0.5f));
+    if (i0 > i1 || j0 > j1) return 0u;
+    const u32 cm = (2u << i1) - (1u << i0);
+    u32 x = (2u << j1) - (1u << j0);           // row bits r -> bit 4r
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return x * cm;
 }
 
-// Does the splat's box {x, y, ex, ey} touch the pixel rectangle [x0,x1] x [y0,y1]?  (NaN-safe towards "yes")
-__device__ __forceinline__ bool splat_hits_rect(const float4 box, const float x0, const float x1, const float y0,
-                                                const float y1) {
-    const float dx = box.x - fminf(fmaxf(box.x, x0), x1);
-    const float dy = box.y - fminf(fmaxf(box.y, y0), y1);
-    return !(fabsf(dx) > box.z) && !(fabsf(dy) > box.w);
+
+// Stage one batch of the tile's list (positions first .. first+cnt-1 in steps of `dir`) into shared memory.
+template <int NT, bool WITH_ID>
+__device__ __forceinline__ void stage_batch(const u32* __restrict__ point_list, const float4* __restrict__ rec,
+                                            const u32 first, const int dir, const int cnt, const float tx0,
+                                            const float ty0, float4* sm_rec, u32* sm_cell, u32* sm_id) {
+    for (int s = threadIdx.x; s < cnt; s += NT) {
+        const u32 id = point_list[first + (u32)(dir * s)];
+        const float4* r = rec + 3 * (size_t)id;
+        const float4 q0 = __ldg(r + 0);
+        const float4 q1 = __ldg(r + 1);
+        if (WITH_ID) sm_id[s] = id;
+        sm_rec[3 * s + 0] = q0;
+        sm_rec[3 * s + 1] = q1;
+        sm_rec[3 * s + 2] = __ldg(r + 2);
+        sm_cell[s] = splat_cellmask(q0, q1, tx0, ty0);
+    }
 }
 
-// Per-batch shared staging: packed 48-byte records + one {x, y, ex, ey} box per splat for the patch test.
-struct BatchSmem {
-    float4 rec[BATCH * 3];
-    float4 box[BATCH];
-};
-
-__global__ void __launch_bounds__(BLEND_THREADS)
+template <int PPT>
+__global__ void __launch_bounds__(256 / PPT)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float4* __restrict__ rec, float* __restrict__ final_T, u32* __restrict__ n_contrib,
                  const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_depth,
                  float* __restrict__ out_alpha) {
-    __shared__ __align__(16) BatchSmem sm;
-    const u32 s_rec = smem_addr(sm.rec);
-    const u32 s_box = smem_addr(sm.box);
+    constexpr int NT = 256 / PPT;
+    __shared__ __align__(16) float4 sm_rec[BATCH * 3];
+    __shared__ u32 sm_cell[BATCH];
+    const u32 s_rec = smem_addr(sm_rec);
+    const u32 s_cell = smem_addr(sm_cell);
 
     const int tid = threadIdx.x, lane = tid & 31;
-    int lx, ly;
-    thread_pixel(tid, lx, ly);
-    const u32 px = blockIdx.x * TILE_X + lx;
-    const u32 py = blockIdx.y * TILE_Y + ly;
-    const u32 pix_id = (u32)W * py + px;
-    const float2 pixf = {(float)px, (float)py};
-    const bool inside = px < (u32)W && py < (u32)H;
-    bool done = !inside;
+    const WarpPixels<PPT> wp(tid >> 5);
+    const u32 px = blockIdx.x * TILE_X + wp.lx(lane);
+    const float pxf = (float)px;
+    const float tx0 = (float)(blockIdx.x * TILE_X), ty0 = (float)(blockIdx.y * TILE_Y);
 
-    // pixel rectangle of this warp's 8x4 patch
-    const int w = tid >> 5;
-    const float wx0 = (float)(blockIdx.x * TILE_X + ((w & 1) << 3)), wx1 = wx0 + 7.0f;
-    const float wy0 = (float)(blockIdx.y * TILE_Y + ((w >> 1) << 2)), wy1 = wy0 + 3.0f;
+    u32 py[PPT];
+    float pyf[PPT];
+    bool inside[PPT], done[PPT];
+    float T[PPT], C0[PPT], C1[PPT], C2[PPT], D[PPT], Wt[PPT];
+    u32 last_contributor[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        py[k] = blockIdx.y * TILE_Y + wp.ly(lane, k);
+        pyf[k] = (float)py[k];
+        inside[k] = px < (u32)W && py[k] < (u32)H;
+        done[k] = !inside[k];
+        T[k] = 1.0f;
+        C0[k] = C1[k] = C2[k] = D[k] = Wt[k] = 0.0f;
+        last_contributor[k] = 0;
+    }
 
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
     const int rounds = ((range.y - range.x + BATCH - 1) / BATCH);
     int toDo = range.y - range.x;
 
-    float T = 1.0f;
-    u32 last_contributor = 0;
-    float C[3] = {0.f, 0.f, 0.f};
-    float D = 0.0f;
-    float weight = 0.0f;
-
     for (int i = 0; i < rounds; i++, toDo -= BATCH) {
-        const int num_done = __syncthreads_count(done);
-        if (num_done == BLEND_THREADS) break;
-
-        const int progress = i * BATCH + tid;
-        if (range.x + progress < range.y) {
-            const u32 id = point_list[range.x + progress];
-            const float4* r = rec + 3 * (size_t)id;
-            const float4 q0 = __ldg(r + 0);
-            const float4 q1 = __ldg(r + 1);
-            sm.rec[3 * tid + 0] = q0;
-            sm.rec[3 * tid + 1] = q1;
-            sm.rec[3 * tid + 2] = __ldg(r + 2);
-            const float2 e = splat_extent(q1);
-            sm.box[tid] = make_float4(q0.x, q0.y, e.x, e.y);
-        }
-        __syncthreads();
-
-        if (__all_sync(0xffffffffu, done)) continue;  // whole warp finished: keep helping with the fetch only
+        bool all_done = true;
+#pragma unroll
+        for (int k = 0; k < PPT; k++) all_done = all_done && done[k];
+        const int num_done = __syncthreads_count(all_done);
+        if (num_done == NT) break;
 
         const int cnt = min(BATCH, toDo);
-        // Per-warp culling: 32 splats are box-tested against the warp's patch at once; only the survivors are
-        // evaluated per pixel, in list order (bit order of the ballot).
+        stage_batch<NT, false>(point_list, rec, range.x + (u32)(i * BATCH), 1, cnt, tx0, ty0, sm_rec, sm_cell, nullptr);
+        __syncthreads();
+
+        // cells of the patches that still have unfinished pixels
+        u32 live = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; k++)
+            if (__ballot_sync(FULL, done[k]) != FULL) live |= 0x33u << wp.cell_shift(k);
+        if (live == 0) continue;  // whole warp finished: keep helping with the fetch only
+
+        // 32 candidates are matched against the warp's live cells at once; only the survivors are evaluated, in
+        // list order (bit order of the ballot), and only for the patches their box reaches.
         for (int base = 0; base < cnt; base += 32) {
             const int jt = base + lane;
-            bool hit = false;
-            if (jt < cnt) hit = splat_hits_rect(lds128(s_box + jt * 16), wx0, wx1, wy0, wy1);
-            u32 mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int j = base + __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (done) continue;
+            u32 h = 0;
+            if (jt < cnt) h = lds32(s_cell + jt * 4) & live;
+            u32 hmask = __ballot_sync(FULL, h != 0u);
+            while (hmask) {
+                const int j = base + __ffs(hmask) - 1;
+                hmask &= hmask - 1;
+                const u32 cm = lds32(s_cell + j * 4) & live;
                 const u32 a = s_rec + j * 48;
                 const float4 q0 = lds128(a);
                 const float4 con_o = lds128(a + 16);
-                const float2 d = {q0.x - pixf.x, q0.y - pixf.y};
-                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                if (power > 0.0f) continue;
-                const float alpha = min(0.99f, con_o.w * exp(power));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = T * (1 - alpha);
-                if (test_T < 0.0001f) {
-                    done = true;
-                    continue;
+                const float dx = q0.x - pxf;
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    if (((cm >> wp.cell_shift(k)) & 0x33u) == 0u) continue;  // warp-uniform
+                    if (done[k]) continue;
+                    const float2 d = {dx, q0.y - pyf[k]};
+                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                    if (power > 0.0f) continue;
+                    const float alpha = min(0.99f, con_o.w * exp(power));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = T[k] * (1 - alpha);
+                    if (test_T < 0.0001f) {
+                        done[k] = true;
+                        continue;
+                    }
+                    const float4 col = lds128(a + 32);
+                    C0[k] += col.x * alpha * T[k];
+                    C1[k] += col.y * alpha * T[k];
+                    C2[k] += col.z * alpha * T[k];
+                    Wt[k] += alpha * T[k];
+                    D[k] += q0.z * alpha * T[k];
+                    T[k] = test_T;
+                    last_contributor[k] = (u32)(i * BATCH + j + 1);
                 }
-                const float4 col = lds128(a + 32);
-                C[0] += col.x * alpha * T;
-                C[1] += col.y * alpha * T;
-                C[2] += col.z * alpha * T;
-                weight += alpha * T;
-                D += q0.z * alpha * T;
-                T = test_T;
-                last_contributor = (u32)(i * BATCH + j + 1);
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            live = 0;
+#pragma unroll
+            for (int k = 0; k < PPT; k++)
+                if (__ballot_sync(FULL, done[k]) != FULL) live |= 0x33u << wp.cell_shift(k);
+            if (live == 0) break;
         }
     }
 
-    if (inside) {
-        final_T[pix_id] = T;
-        n_contrib[pix_id] = last_contributor;
-        const size_t plane = (size_t)H * W;
-        out_color[0 * plane + pix_id] = C[0] + T * bg_color[0];
-        out_color[1 * plane + pix_id] = C[1] + T * bg_color[1];
-        out_color[2 * plane + pix_id] = C[2] + T * bg_color[2];
-        out_depth[pix_id] = D;
-        out_alpha[pix_id] = weight;
+    const size_t plane = (size_t)H * W;
+    const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        if (!inside[k]) continue;
+        const u32 pix_id = (u32)W * py[k] + px;
+        final_T[pix_id] = T[k];
+        n_contrib[pix_id] = last_contributor[k];
+        out_color[0 * plane + pix_id] = C0[k] + T[k] * bg0;
+        out_color[1 * plane + pix_id] = C1[k] + T[k] * bg1;
+        out_color[2 * plane + pix_id] = C2[k] + T[k] * bg2;
+        out_depth[pix_id] = D[k];
+        out_alpha[pix_id] = Wt[k];
     }
 }
 
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
     dim3 grid(tiles_x(W), tiles_y(H), 1);
-    blend_fwd_kernel<<<grid, BLEND_THREADS, 0, st>>>(img.ranges, b.point_list, W, H, g.rec, img.final_T,
-                                                    img.n_contrib, bg, out_color, out_depth, out_alpha);
+#define BAGS_FWD(PPT)                                                                                            \
+    blend_fwd_kernel<PPT><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, g.rec, img.final_T,        \
+                                                     img.n_contrib, bg, out_color, out_depth, out_alpha)
+    if (g_fwd_ppt == 4) BAGS_FWD(4);
+    else if (g_fwd_ppt == 2) BAGS_FWD(2);
+    else BAGS_FWD(1);
+#undef BAGS_FWD
     BAGS_LAUNCH_OK("blend_fwd_kernel");
     return 0;
 }
@@ -189,135 +255,116 @@ int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, Im
 // Backward
 // =================================================================================================================
 
-// Transposed butterfly: every lane holds 16 partial values; on return lane L holds the warp-wide sum of value
-// ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)  (so lane 2k holds value k).  16 shuffles in total.
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
-    float a8[8];
-    {
-        const bool up = lane & 16;
+// One level of the transposed butterfly: N partial values per lane -> N/2, exchanging with lane ^ OFF.  Lanes with
+// bit OFF set keep the upper half of the slots.
+template <int N, int OFF>
+__device__ __forceinline__ void bfly(const float (&in)[N], float (&out)[N / 2], const int lane) {
+    const bool up = lane & OFF;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float send = up ? v[k] : v[k + 8];
-            const float keep = up ? v[k + 8] : v[k];
-            a8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
+    for (int k = 0; k < N / 2; k++) {
+        const float send = up ? in[k] : in[k + N / 2];
+        const float keep = up ? in[k + N / 2] : in[k];
+        out[k] = keep + __shfl_xor_sync(FULL, send, OFF);
     }
-    float a4[4];
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float send = up ? a8[k] : a8[k + 4];
-            const float keep = up ? a8[k + 4] : a8[k];
-            a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    float a2[2];
-    {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const float send = up ? a4[k] : a4[k + 2];
-            const float keep = up ? a4[k + 2] : a4[k];
-            a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    float a1;
-    {
-        const bool up = lane & 2;
-        const float send = up ? a2[0] : a2[1];
-        const float keep = up ? a2[1] : a2[0];
-        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-    return a1;
 }
 
-struct BatchSmemBwd {
-    float4 rec[BATCH * 3];
-    float4 box[BATCH];
-    u32 id[BATCH];
-};
+// Warp sum of the 16 slots of `v`, added into the 16-float record `dst` (slots 0..12 are used; 13..15 are zero
+// padding and never written).  16 + 3 shuffles; lane 2k ends up with slot k.
+__device__ __forceinline__ void warp_reduce_commit(float (&v)[16], const int lane, float* dst) {
+    float a8[8], a4[4], a2[2], a1[1];
+    bfly<16, 16>(v, a8, lane);
+    bfly<8, 8>(a8, a4, lane);
+    bfly<4, 4>(a4, a2, lane);
+    bfly<2, 2>(a2, a1, lane);
+    float r0 = a1[0];
+    r0 += __shfl_xor_sync(FULL, r0, 1);
+    const float r1 = __shfl_down_sync(FULL, r0, 2);
+    const float r2 = __shfl_down_sync(FULL, r0, 4);
+    const float r3 = __shfl_down_sync(FULL, r0, 6);
+    if (!(lane & 7)) {
+        if (lane < 24) atomicAdd(reinterpret_cast<float4*>(dst + (lane >> 1)), make_float4(r0, r1, r2, r3));
+        else atomicAdd(dst + GA_COV, r0);
+    }
+}
 
-__global__ void __launch_bounds__(BLEND_THREADS)
+#ifdef BAGS_STATS
+__device__ unsigned long long g_stats[64];
+#endif
+
+template <int PPT>
+__global__ void __launch_bounds__(256 / PPT)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float* __restrict__ bg_color, const float4* __restrict__ rec,
                  const float* __restrict__ final_Ts, const u32* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
                  const float* __restrict__ dL_dalphas, float* __restrict__ gacc) {
-    __shared__ __align__(16) BatchSmemBwd sm;
-    __shared__ u32 s_wmax[BLEND_THREADS / 32];
-    const u32 s_rec = smem_addr(sm.rec);
-    const u32 s_box = smem_addr(sm.box);
-    const u32 s_id = smem_addr(sm.id);
+    constexpr int NT = 256 / PPT;
+    constexpr int NW = NT / 32;
+    __shared__ __align__(16) float4 sm_rec[BATCH * 3];
+    __shared__ u32 sm_cell[BATCH];
+    __shared__ u32 sm_id[BATCH];
+    __shared__ u32 s_wmax[NW];
+    const u32 s_rec = smem_addr(sm_rec);
+    const u32 s_cell = smem_addr(sm_cell);
+    const u32 s_id = smem_addr(sm_id);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int lx, ly;
-    thread_pixel(tid, lx, ly);
-    const u32 px = blockIdx.x * TILE_X + lx;
-    const u32 py = blockIdx.y * TILE_Y + ly;
-    const u32 pix_id = (u32)W * py + px;
-    const float2 pixf = {(float)px, (float)py};
-    const bool inside = px < (u32)W && py < (u32)H;
-
+    const WarpPixels<PPT> wp(warp);
+    const u32 px = blockIdx.x * TILE_X + wp.lx(lane);
+    const float pxf = (float)px;
+    const float tx0 = (float)(blockIdx.x * TILE_X), ty0 = (float)(blockIdx.y * TILE_Y);
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+    const size_t plane = (size_t)H * W;
+    const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
-    const float T_final = inside ? final_Ts[pix_id] : 0;
-    float T = T_final;
-    const u32 last_contributor = inside ? n_contrib[pix_id] : 0;
-
-    float accum_rec[3] = {0.f, 0.f, 0.f};
-    float dL_dpixel[3] = {0.f, 0.f, 0.f};
-    float accum_depth_rec = 0;
-    float dL_dpixel_depth = 0;
-    float accum_alpha_rec = 0;
-    float dL_dweight_alpha = 0;
-    if (inside) {
-        const size_t plane = (size_t)H * W;
+    // per-pixel state (registers; every loop over k is fully unrolled)
+    float pyf[PPT], T[PPT], ar0[PPT], ar1[PPT], ar2[PPT], ad[PPT], aa[PPT];
+    float g0[PPT], g1[PPT], g2[PPT], gd[PPT], gw[PPT], nTbg[PPT];
+    u32 last_contributor[PPT], pmax[PPT];
+    u32 warp_max = 0;
 #pragma unroll
-        for (int i = 0; i < 3; i++) dL_dpixel[i] = dL_dpixels[i * plane + pix_id];
-        dL_dpixel_depth = dL_dpixel_depths[pix_id];
-        dL_dweight_alpha = dL_dalphas[pix_id];
+    for (int k = 0; k < PPT; k++) {
+        const u32 py = blockIdx.y * TILE_Y + wp.ly(lane, k);
+        pyf[k] = (float)py;
+        const bool inside = px < (u32)W && py < (u32)H;
+        const u32 pix_id = (u32)W * py + px;
+        const float T_final = inside ? final_Ts[pix_id] : 0;
+        T[k] = T_final;
+        last_contributor[k] = inside ? n_contrib[pix_id] : 0;
+        g0[k] = g1[k] = g2[k] = gd[k] = gw[k] = 0.f;
+        if (inside) {
+            g0[k] = dL_dpixels[0 * plane + pix_id];
+            g1[k] = dL_dpixels[1 * plane + pix_id];
+            g2[k] = dL_dpixels[2 * plane + pix_id];
+            gd[k] = dL_dpixel_depths[pix_id];
+            gw[k] = dL_dalphas[pix_id];
+        }
+        float bg_dot_dpixel = 0;
+        bg_dot_dpixel += bg0 * g0[k];
+        bg_dot_dpixel += bg1 * g1[k];
+        bg_dot_dpixel += bg2 * g2[k];
+        nTbg[k] = -T_final * bg_dot_dpixel;
+        ar0[k] = ar1[k] = ar2[k] = ad[k] = aa[k] = 0.f;
+        // Only list positions below the largest n_contrib of the patch / warp / CTA can contribute.
+        pmax[k] = __reduce_max_sync(FULL, last_contributor[k]);
+        warp_max = max(warp_max, pmax[k]);
     }
-    float last_alpha = 0;
-    float last_color[3] = {0.f, 0.f, 0.f};
-    float last_depth = 0;
-    float bg_dot_dpixel = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) bg_dot_dpixel += bg_color[i] * dL_dpixel[i];
-    const float neg_Tfinal_bg = -T_final * bg_dot_dpixel;
+    const u32 warp_cells = wp.cells();
 
     const float ddelx_dx = 0.5 * W;
     const float ddely_dy = 0.5 * H;
 
-    // pixel rectangle of this warp's 8x4 patch (per-warp culling, see splat_extent)
-    const float wx0 = (float)(blockIdx.x * TILE_X + ((warp & 1) << 3)), wx1 = wx0 + 7.0f;
-    const float wy0 = (float)(blockIdx.y * TILE_Y + ((warp >> 1) << 2)), wy1 = wy0 + 3.0f;
-
-    // Only list positions below the largest n_contrib of the CTA (resp. warp) can contribute.
-    const u32 warp_max = __reduce_max_sync(0xffffffffu, last_contributor);
     if (lane == 0) s_wmax[warp] = warp_max;
     __syncthreads();
     u32 block_max = 0;
 #pragma unroll
-    for (int w = 0; w < BLEND_THREADS / 32; w++) block_max = max(block_max, s_wmax[w]);
+    for (int w = 0; w < NW; w++) block_max = max(block_max, s_wmax[w]);
 
     // walk positions [0, block_max) back to front in chunks of BATCH; slot j of a chunk is position hi-1-j
     for (int hi = (int)block_max; hi > 0; hi -= BATCH) {
         const int cnt = min(BATCH, hi);
         __syncthreads();  // everyone is done with the previous chunk
-        if (tid < cnt) {
-            const u32 id = point_list[range.x + (u32)(hi - 1 - tid)];
-            const float4* r = rec + 3 * (size_t)id;
-            const float4 q0 = __ldg(r + 0);
-            const float4 q1 = __ldg(r + 1);
-            sm.id[tid] = id;
-            sm.rec[3 * tid + 0] = q0;
-            sm.rec[3 * tid + 1] = q1;
-            sm.rec[3 * tid + 2] = __ldg(r + 2);
-            const float2 e = splat_extent(q1);
-            sm.box[tid] = make_float4(q0.x, q0.y, e.x, e.y);
-        }
+        stage_batch<NT, true>(point_list, rec, range.x + (u32)(hi - 1), -1, cnt, tx0, ty0, sm_rec, sm_cell, sm_id);
         __syncthreads();
 
         // first slot this warp can contribute to: position hi-1-j < warp_max  <=>  j >= hi-warp_max
@@ -325,84 +372,85 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
         if (j0 < 0) j0 = 0;
         for (int base = j0 & ~31; base < cnt; base += 32) {
             const int jt = base + lane;
-            bool hit = false;
-            if (jt >= j0 && jt < cnt) hit = splat_hits_rect(lds128(s_box + jt * 16), wx0, wx1, wy0, wy1);
-            u32 hmask = __ballot_sync(0xffffffffu, hit);
+            u32 h = 0;
+            if (jt >= j0 && jt < cnt) h = lds32(s_cell + jt * 4) & warp_cells;
+            u32 hmask = __ballot_sync(FULL, h != 0u);
             while (hmask) {
                 const int j = base + __ffs(hmask) - 1;
                 hmask &= hmask - 1;
                 const u32 pos = (u32)(hi - 1 - j);
+                const u32 cm = lds32(s_cell + j * 4);
                 const u32 a = s_rec + j * 48;
                 const float4 q0 = lds128(a);
                 const float4 con_o = lds128(a + 16);
-                const float2 d = {q0.x - pixf.x, q0.y - pixf.y};
-                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                const float G = exp(power);
-                const float alpha = min(0.99f, con_o.w * G);
-                const bool valid = (pos < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                const u32 vmask = __ballot_sync(0xffffffffu, valid);
-                if (vmask == 0) continue;
+                const float dx = q0.x - pxf;
 
                 float v[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) v[k] = 0.f;
-                if (valid) {
+                for (int s = 0; s < 16; s++) v[s] = 0.f;
+                bool any_valid = false;
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    // warp-uniform: does the splat's box reach this patch, and is the position still live there?
+                    if (((cm >> wp.cell_shift(k)) & 0x33u) == 0u || pos >= pmax[k]) continue;
+                    const float2 d = {dx, q0.y - pyf[k]};
+                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                    const float Gv = exp(power);
+                    const float alpha = min(0.99f, con_o.w * Gv);
+                    const bool valid = (pos < last_contributor[k]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    if (!valid) continue;
+                    any_valid = true;
                     // T_j = T_{j+1} / (1 - alpha); one reciprocal serves both divisions of backward.cu:1051,1090
                     const float rcp = __fdividef(1.0f, 1.f - alpha);
-                    T = T * rcp;
-                    const float dchannel_dcolor = alpha * T;
+                    T[k] = T[k] * rcp;
+                    const float dchannel_dcolor = alpha * T[k];
                     const float4 col = lds128(a + 32);
-                    const float c3[3] = {col.x, col.y, col.z};
+                    const float one_minus_alpha = 1.f - alpha;
                     float dL_dalpha = 0.0f;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        const float c = c3[ch];
-                        accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                        last_color[ch] = c;
-                        const float dL_dchannel = dL_dpixel[ch];
-                        dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
-                        v[GA_R + ch] = dchannel_dcolor * dL_dchannel;
-                    }
-                    const float c_d = q0.z;
-                    accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-                    last_depth = c_d;
-                    dL_dalpha += (c_d - accum_depth_rec) * dL_dpixel_depth;
-                    v[GA_DEPTH] = dchannel_dcolor * dL_dpixel_depth;
+                    // ar* hold "colour behind this splat" (the reference's accum_rec after its update)
+                    dL_dalpha += (col.x - ar0[k]) * g0[k];
+                    dL_dalpha += (col.y - ar1[k]) * g1[k];
+                    dL_dalpha += (col.z - ar2[k]) * g2[k];
+                    v[GA_R] += dchannel_dcolor * g0[k];
+                    v[GA_G] += dchannel_dcolor * g1[k];
+                    v[GA_B] += dchannel_dcolor * g2[k];
+                    ar0[k] = alpha * col.x + one_minus_alpha * ar0[k];
+                    ar1[k] = alpha * col.y + one_minus_alpha * ar1[k];
+                    ar2[k] = alpha * col.z + one_minus_alpha * ar2[k];
+                    dL_dalpha += (q0.z - ad[k]) * gd[k];
+                    v[GA_DEPTH] += dchannel_dcolor * gd[k];
+                    ad[k] = alpha * q0.z + one_minus_alpha * ad[k];
+                    dL_dalpha += (1 - aa[k]) * gw[k];
+                    aa[k] = alpha + one_minus_alpha * aa[k];
 
-                    accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
-                    dL_dalpha += (1 - accum_alpha_rec) * dL_dweight_alpha;
-
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += neg_Tfinal_bg * rcp;
+                    dL_dalpha *= T[k];
+                    dL_dalpha += nTbg[k] * rcp;
 
                     const float dL_dG = con_o.w * dL_dalpha;
-                    const float gdx = G * d.x;
-                    const float gdy = G * d.y;
+                    const float gdx = Gv * d.x;
+                    const float gdy = Gv * d.y;
                     const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
                     const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
                     const float mx = dL_dG * dG_ddelx * ddelx_dx;
                     const float my = dL_dG * dG_ddely * ddely_dy;
-                    v[GA_MX] = mx;
-                    v[GA_MY] = my;
-                    v[GA_AMX] = fabsf(mx);
-                    v[GA_AMY] = fabsf(my);
-                    v[GA_CA] = -0.5f * gdx * d.x * dL_dG;
-                    v[GA_CB] = -0.5f * gdx * d.y * dL_dG;
-                    v[GA_CC] = -0.5f * gdy * d.y * dL_dG;
-                    v[GA_OP] = G * dL_dalpha;
+                    v[GA_MX] += mx;
+                    v[GA_MY] += my;
+                    v[GA_AMX] += fabsf(mx);
+                    v[GA_AMY] += fabsf(my);
+                    v[GA_CA] += -0.5f * gdx * d.x * dL_dG;
+                    v[GA_CB] += -0.5f * gdx * d.y * dL_dG;
+                    v[GA_CC] += -0.5f * gdy * d.y * dL_dG;
+                    v[GA_OP] += Gv * dL_dalpha;
+                    v[GA_COV] += con_o.x + con_o.z;  // diagnostic trace, once per contributing pixel (backward.cu:1116)
                 }
-                // warp sum of the 12 terms; lane 2k holds term k.  Lanes 0, 8, 16 gather their four neighbours and
-                // commit one 128-bit vector reduction each; lane 24 adds the covariance diagnostic.
-                const float r0 = warp_reduce16(v, lane);
-                const float r1 = __shfl_down_sync(0xffffffffu, r0, 2);
-                const float r2 = __shfl_down_sync(0xffffffffu, r0, 4);
-                const float r3 = __shfl_down_sync(0xffffffffu, r0, 6);
-                if ((lane & 7) == 0) {
-                    float* dst = gacc + (size_t)lds32(s_id + j * 4) * GACC_STRIDE;
-                    if (lane < 24) atomicAdd(reinterpret_cast<float4*>(dst + (lane >> 1)), make_float4(r0, r1, r2, r3));
-                    else atomicAdd(dst + GA_COV, (float)__popc(vmask) * (con_o.x + con_o.z));
+#ifdef BAGS_STATS
+                {
+                    const u32 vm = __ballot_sync(FULL, any_valid);
+                    if (lane == 0) atomicAdd(&g_stats[__popc(vm)], 1ull);
                 }
+#endif
+                if (!__any_sync(FULL, any_valid)) continue;
+                warp_reduce_commit(v, lane, gacc + (size_t)lds32(s_id + j * 4) * GACC_STRIDE);
             }
         }
     }
@@ -412,10 +460,35 @@ int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, co
                      const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalpha, float* gacc,
                      cudaStream_t st) {
     dim3 grid(tiles_x(W), tiles_y(H), 1);
-    blend_bwd_kernel<<<grid, BLEND_THREADS, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec, img.final_T,
-                                                    img.n_contrib, dL_dpix, dL_dpix_depth, dL_dalpha, gacc);
+#define BAGS_BWD(PPT)                                                                                            \
+    blend_bwd_kernel<PPT><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec, img.final_T,    \
+                                                     img.n_contrib, dL_dpix, dL_dpix_depth, dL_dalpha, gacc)
+    if (g_bwd_ppt == 4) BAGS_BWD(4);
+    else if (g_bwd_ppt == 2) BAGS_BWD(2);
+    else BAGS_BWD(1);
+#undef BAGS_BWD
     BAGS_LAUNCH_OK("blend_bwd_kernel");
     return 0;
 }
 
 }  // namespace bags
+
+#ifdef BAGS_STATS
+extern "C" int bags_debug_stats(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, bags::g_stats, sizeof(bags::g_stats));
+    if (reset) {
+        unsigned long long z[64] = {0};
+        cudaMemcpyToSymbol(bags::g_stats, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
+extern "C" int bags_set_tuning(int knob, int value) {
+    int* target = knob == BAGS_TUNE_BLEND_FWD_PPT ? &bags::g_fwd_ppt : knob == BAGS_TUNE_BLEND_BWD_PPT ? &bags::g_bwd_ppt : nullptr;
+    if (!target) return BAGS_E_INVALID;
+    const int prev = *target;
+    if (value == 1 || value == 2 || value == 4) *target = value;
+    return prev;
+}

@@ -144,6 +144,28 @@ def test_against_live_reference(case):
 
 
 @pytest.mark.skipif(not pc.ref_available(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("ppt", [1, 2, 4])
+@pytest.mark.parametrize("case", [LIVE_CASES[1], LIVE_CASES[3]], ids=["bg_shift", "dense_big_splats"])
+def test_blend_pixels_per_thread_live(case, ppt):
+    """Every pixels-per-thread variant of the blend kernels (bags_set_tuning) meets the same bars."""
+    import bags_capi
+    L = bags_capi.lib()
+    cam = S.make_camera(case["W"], case["H"])
+    gs = S.make_gaussians(case["P"], cam, scale=case["scale"])
+    up = S.make_upstream(case["H"], case["W"])
+    kw = dict(sh_degree=case.get("sh_degree", 3), bg=case.get("bg", (0, 0, 0)), shift=case.get("shift", (0, 0, 0)),
+              scale_modifier=case.get("scale_modifier", 1.0))
+    prev = [L.bags_set_tuning(knob, ppt) for knob in (0, 1)]
+    try:
+        o = pc.run_view(pc.load_ours(), cam, gs, up, dev(), **kw)
+    finally:
+        for knob in (0, 1):
+            L.bags_set_tuning(knob, prev[knob])
+    r = pc.run_view(pc.load_ref(), cam, gs, up, dev(), **kw)
+    _check_live(o, r, (cam, gs, up, kw))
+
+
+@pytest.mark.skipif(not pc.ref_available(), reason="reference build (oracle/_ref) not present")
 def test_precomputed_colors_and_covariance_live():
     c = MG.CASES["tiny_precomp"]
     cam, gs, up, kw = MG.build_case(c)
