@@ -34,8 +34,8 @@ SCALE = 0.004     # median Gaussian scale of the synthetic scenes (gi
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(S.CONFIGS))
     ap.add_argument("--views-per-gpu", type=int, default=4)
@@ -73,6 +73,18 @@ class ClockSampler:
                                        "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def wait_first_sample(self, timeout=15.0):
+        """nvidia-smi takes a second or two to initialise NVML (and perturbs kernel launches while it does): do not
+        start timing before it has printed its first line."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.05)
 
     def stop(self):
         if self.p is None:
@@ -253,27 +265,30 @@ def main():
     if args.impl == "ours":
         import bags_capi as capi
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
+    if sampler is not None:
+        sampler.wait_first_sample()
 
-    # workload statistics from one forward (V, R)
-    with torch.no_grad():
-        c, radii, d, w_, _ = render(views[0])
-    V = int((radii > 0).sum())
+    # workload statistics: visible Gaussians V and tile instances R of every view of this rank (means are used
+    # for the algorithmic byte counts, since the stage times below are averages over the same views)
+    Vs, Rs = [], []
+    for vw in views:
+        c, radii, d, w_, _ = render(vw)
+        Vs.append(int((radii > 0).sum()))
+        Rs.append(int(c.grad_fn.num_rendered))
+        del c, radii, d, w_
+    V = sum(Vs) / len(Vs)
+    R = sum(Rs) / len(Rs)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches = None
     if capi is not None:
-        capi.lib().bags_profile_enable(1)
-        capi.profile_read()
         launches0 = capi.lib().bags_launch_count()
     ms = timed(step_device, args.steps)
-    stage_ms, stage_calls, launches = {}, {}, None
     if capi is not None:
-        stage_ms, stage_calls = capi.profile_read()
-        capi.lib().bags_profile_enable(0)
         launches = int(capi.lib().bags_launch_count() - launches0)
-    clocks = sampler.stop() if sampler is not None else None
 
     e2e = None
     if not args.no_e2e:
@@ -283,6 +298,19 @@ def main():
         e2e = {"value": nviews * args.steps / (ms_e2e / 1e3), "unit": "views/s",
                "h2d_bytes_per_step": len(views) * 3 * N * 4, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}
+    clocks = sampler.stop() if sampler is not None else None
+
+    # per-stage CUDA-event times (events on the launching stream, recorded inside the library) in a separate short
+    # pass, so that the event records do not sit in the timed region above
+    stage_ms, stage_calls = {}, {}
+    if capi is not None:
+        capi.lib().bags_profile_enable(1)
+        capi.profile_read()
+        for _ in range(3):
+            step_device()
+        torch.cuda.synchronize()
+        stage_ms, stage_calls = capi.profile_read()
+        capi.lib().bags_profile_enable(0)
 
     if rank != 0:
         if use_dist:
@@ -297,7 +325,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {P} random Gaussians SH3, {W}x{H}, {vpg} views/GPU/step "
                                f"(fwd+bwd incl. pose/intrinsic grads), median scale {SCALE}",
-                   "views_per_step": nviews, "visible": V, "l2": "per-view working set (236 B x P inputs + state) "
+                   "views_per_step": nviews, "visible_mean": V, "tile_instances_mean": R, "l2": "per-view working set (236 B x P inputs + state) "
                    "exceeds the 126 MB L2; no explicit flush", "parallelism": f"view-dp{world}"},
         "clocks": clocks,
     }
@@ -323,24 +351,27 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # num_rendered of this rank's first view, through the autograd ctx
-    color, radii, depth, weights, _ = render(views[0])
-    R = int(color.grad_fn.num_rendered)
     Tt = ((W + 15) // 16) * ((H + 15) // 16)
     ab = algorithmic_bytes(P, V, R, N, Tt)
     stage_bytes = {"preprocess": ab["preprocess"], "depth_sort": ab["scan"], "emit": ab["duplicate"],
                    "tile_sort": ab["sort"], "ranges": ab["ranges"], "blend_fwd": ab["blend_fwd"],
                    "blend_bwd": ab["blend_bwd"], "preprocess_bwd": ab["preprocess_bwd"], "bwd_clear": 0}
     stages = {}
+    nviews_prof = max(stage_calls.get("preprocess", 0), 1)      # one preprocess per view; a stage may record twice
     for k, tot in stage_ms.items():
-        n = max(stage_calls.get(k, 0), 1)
-        avg = tot / n
+        avg = tot / nviews_prof
         gbs = stage_bytes.get(k, 0) / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
         stages[k] = {"ms": round(avg, 4), "alg_GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
     dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
+    traffic = None
+    try:  # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     if dom:
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["alg_GBps"], "peak": peak,
-                            "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": None,
+                            "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic,
                             "peak_source": peak_src, "R": R, "V": V,
                             "note": "blend kernels are FP32-issue/L2-atomic bound, not HBM bound; see stages + profiles/"}
         pb = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges"]

@@ -321,6 +321,14 @@ extern "C" int bags_rasterize_forward(
     }
     if (rc) return rc;
 
+    // offsets of every Gaussian's tile instances (depth order) go to the key buffer the sort did not end in; this
+    // does not need num_rendered, so it also runs while the host waits
+    u32* offsets = (sorted_keys == g.key_a) ? g.key_b : g.key_a;
+    prof_begin(BAGS_STAGE_EMIT, st);
+    rc = launch_emit_scan(P, g, sorted_idx, offsets, st);
+    prof_end(BAGS_STAGE_EMIT, st);
+    if (rc) return rc;
+
     BAGS_CUDA_OK(cudaEventSynchronize(ctx->ev));
     const unsigned long long R64 = *ctx->pinned;
     if (R64 >= (1ull << 30)) {
@@ -341,7 +349,7 @@ extern "C" int bags_rasterize_forward(
     if (R > 0) {
         {
             ProfScope ps(BAGS_STAGE_EMIT, st);
-            rc = launch_emit(P, g, sorted_idx, b, tiles_x(width), st);
+            rc = launch_emit_fill(P, R, g, sorted_idx, offsets, b, tiles_x(width), st);
         }
         if (rc) return rc;
         u32 *fk, *fv;

@@ -7,13 +7,12 @@
 //
 //   1. depth sort   : stable sort of the P Gaussians by their 32 depth bits (culled ones carry 0xFFFFFFFF),
 //                     4 x 8-bit onesweep passes over P x 8 B  -> order (depth, id);
-//   2. emit         : walk Gaussians in that order, append (tile, id) for every tile of the stored rectangle
-//                     (y outer, x inner like rasterizer_impl.cu:98-108); output offsets come from a decoupled
-//                     look-back scan fused into the same kernel (no separate InclusiveSum, no offsets array);
+//   2. emit         : in that order, append (tile, id) for every tile of the stored rectangle (y outer, x inner
+//                     like rasterizer_impl.cu:98-108): a decoupled look-back scan of the tile counts, then a
+//                     slot-parallel fill (one thread per output instance);
 //   3. tile sort    : stable sort of the R instances by tile id only, ceil(bit/8) (= 2) passes over R x 8 B
 //                     -> order (tile, depth, id), identical to the reference's point_list;
-//   4. ranges       : per-tile binary search in the sorted tile ids; empty tiles get (0,0) like the reference's
-//                     cudaMemset.
+//   4. ranges       : boundaries of the sorted tile ids; empty tiles keep (0,0) like the reference's cudaMemset.
 //
 // Per tile instance this moves 4 (histogram) + 2 x 16 (passes) + 8 (emit) bytes instead of the reference's
 // 12 (emit) + 8 + 6 x 24 (sort) + 8 (ranges).
@@ -23,20 +22,22 @@
 namespace bags {
 
 // =================================================================================================================
-// Onesweep radix sort (u32 keys, u32 values), 8-bit digits, one CTA per 8192-key tile, decoupled look-back.
+// Onesweep radix sort (u32 keys, u32 values), 8-bit digits, one CTA per 4096-key tile (4 CTAs per SM), decoupled
+// look-back with several predecessors in flight per round.
 // =================================================================================================================
-constexpr size_t SORT_SMEM_BYTES = (SORT_TILE + SORT_WARPS * RADIX + 2 * RADIX + 8) * sizeof(u32);
+constexpr size_t SORT_SMEM_BYTES = (2 * SORT_TILE + SORT_WARPS * RADIX + 2 * RADIX + 8) * sizeof(u32);
+constexpr int SORT_LOOKBACK = 8;     // predecessor status words fetched per look-back round (memory-level parallelism)
 constexpr u32 FLAG_AGG = 1u << 30;   // tile aggregate available
 constexpr u32 FLAG_INCL = 2u << 30;  // inclusive prefix available
 constexpr u32 VAL_MASK = (1u << 30) - 1;
 
 __device__ __forceinline__ u32 ld_volatile_u32(const u32* p) {
     u32 v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u32(u32* p, u32 v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Histograms of every digit position in one read of the keys.
@@ -63,7 +64,22 @@ sort_hist_kernel(const u32* __restrict__ keys, int n, int begin_bit, int end_bit
     }
 }
 
-// Exclusive scan of 256 values held one per thread by the first 256 threads of the CTA (8 warps).
+// Lanes of the warp holding the same digit as the caller: one ballot per digit bit (the match.any instruction has a
+// far lower throughput than `bits` votes).
+__device__ __forceinline__ u32 match_digit(const u32 d, const int bits) {
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; b++) {
+        if (b < bits) {
+            const bool set = (d >> b) & 1u;
+            const u32 vote = __ballot_sync(0xffffffffu, set);
+            peers &= set ? vote : ~vote;
+        }
+    }
+    return peers;
+}
+
+// Exclusive scan of 256 values held one per thread by the 256 threads of the CTA (8 warps).
 __device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32* warp_tot /*[8] smem*/, int tid) {
     const int lane = tid & 31, w = tid >> 5;
     u32 inc = v;
@@ -83,17 +99,19 @@ __device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32* warp_tot /*[8] sm
 }
 
 template <bool IOTA>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 4)
 onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, u32* __restrict__ keys_out,
                      u32* __restrict__ vals_out, int n, int shift, int bits, const u32* __restrict__ ghist,
                      u32* __restrict__ tile_counter, u32* __restrict__ status) {
     extern __shared__ u32 sort_smem[];
-    u32* s_buf = sort_smem;                                              // [SORT_TILE] staging, locally sorted order
-    u32 (*s_wcnt)[RADIX] = reinterpret_cast<u32 (*)[RADIX]>(s_buf + SORT_TILE);  // [SORT_WARPS][RADIX]
-    u32* s_local = s_buf + SORT_TILE + SORT_WARPS * RADIX;               // [RADIX] digit offset inside the tile
+    u32* s_keys = sort_smem;                                             // [SORT_TILE] keys in locally sorted order
+    u32* s_vals = s_keys + SORT_TILE;                                    // [SORT_TILE] their values
+    u32 (*s_wcnt)[RADIX] = reinterpret_cast<u32 (*)[RADIX]>(s_vals + SORT_TILE);  // [SORT_WARPS][RADIX]
+    u32* s_local = s_vals + SORT_TILE + SORT_WARPS * RADIX;              // [RADIX] digit offset inside the tile
     u32* s_gbase = s_local + RADIX;                                      // [RADIX] global index of local position 0
     u32* s_wtot = s_gbase + RADIX;                                       // [8]
     __shared__ u32 s_tile;
+    static_assert(SORT_THREADS == RADIX, "one thread per digit in the look-back");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
@@ -114,29 +132,39 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
         key[i] = (loc < nvalid) ? keys_in[tile_base + loc] : 0xFFFFFFFFu;
     }
 
-    // ---- rank inside the warp, in memory order, with match_any ----
+    // ---- rank inside the warp, in memory order ----
+    // Per item: the lanes holding the same digit (one ballot per digit bit), the number of them below this lane, and
+    // one shared-memory atomic by the leader lane that reserves the group's slots in the warp's digit counter.  The
+    // atomics of one warp reach the shared-memory unit in program order, so equal digits of later items see the
+    // counts of earlier ones without a warp barrier per item, and groups of items pipeline instead of forming a
+    // chain of 16 load-add-store-shuffle round trips.
     const u32 lt_mask = (1u << lane) - 1u;
     u32* wc = s_wcnt[warp];
+    constexpr int RANK_GROUP = 4;   // items in flight between the atomics and the shuffles that distribute them
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++) {
-        int loc = wbase + i * 32;
-        u32 d = (loc < nvalid) ? ((key[i] >> shift) & mask) : (u32)(RADIX - 1);
-        u32 peers = __match_any_sync(0xffffffffu, d);
-        u32 lower = __popc(peers & lt_mask);
-        int leader = __ffs(peers) - 1;
-        u32 old = 0;
-        if (lane == leader) {
-            old = wc[d];
-            wc[d] = old + __popc(peers);
+    for (int i0 = 0; i0 < SORT_ITEMS; i0 += RANK_GROUP) {
+        u32 old[RANK_GROUP];
+#pragma unroll
+        for (int k = 0; k < RANK_GROUP; k++) {
+            const int i = i0 + k;
+            int loc = wbase + i * 32;
+            u32 d = (loc < nvalid) ? ((key[i] >> shift) & mask) : (u32)(RADIX - 1);
+            u32 peers = match_digit(d, bits);
+            u32 lower = __popc(peers & lt_mask);
+            old[k] = 0;
+            if (lower == 0) old[k] = atomicAdd(&wc[d], (u32)__popc(peers));   // lowest lane of the group leads
+            rank[i] = lower | ((u32)(__ffs(peers) - 1) << 8);
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[i] = old + lower;
-        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < RANK_GROUP; k++) {
+            const int i = i0 + k;
+            rank[i] = __shfl_sync(0xffffffffu, old[k], (int)(rank[i] >> 8)) + (rank[i] & 0xffu);
+        }
     }
     __syncthreads();
 
-    // ---- per digit: exclusive offsets across warps, tile count, look-back, global base ----
-    if (tid < RADIX) {
+    // ---- per digit (one thread each): exclusive offsets across warps, tile count, look-back, global base ----
+    {
         u32 sum = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; w++) {
@@ -148,14 +176,26 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
         u32 excl = 0;
         if (tile > 0) {
             st_volatile_u32(st, sum | FLAG_AGG);
-            const u32* look = st - RADIX;
-            while (true) {
-                u32 s = ld_volatile_u32(look);
-                u32 f = s & ~VAL_MASK;
-                if (f == 0) continue;
-                excl += s & VAL_MASK;
-                if (f == FLAG_INCL) break;
-                look -= RADIX;
+            // Decoupled look-back, SORT_LOOKBACK predecessors per round: the loads of a round are independent, so a
+            // walk over k tiles costs about k / SORT_LOOKBACK memory round trips instead of k.
+            int look = (int)tile - 1;
+            bool done = false;
+            while (!done) {
+                u32 sw[SORT_LOOKBACK];
+#pragma unroll
+                for (int k = 0; k < SORT_LOOKBACK; k++) {
+                    const int t = look - k;
+                    sw[k] = (t >= 0) ? ld_volatile_u32(status + (size_t)t * RADIX + tid) : FLAG_INCL;
+                }
+#pragma unroll
+                for (int k = 0; k < SORT_LOOKBACK; k++) {
+                    if (done) continue;
+                    u32 v = sw[k];
+                    while ((v & ~VAL_MASK) == 0) v = ld_volatile_u32(status + (size_t)(look - k) * RADIX + tid);
+                    excl += v & VAL_MASK;
+                    if ((v & ~VAL_MASK) == FLAG_INCL) done = true;
+                }
+                look -= SORT_LOOKBACK;
             }
         }
         st_volatile_u32(st, ((excl + sum) & VAL_MASK) | FLAG_INCL);
@@ -168,40 +208,28 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     }
     __syncthreads();
 
-    // ---- scatter keys to their locally sorted position, then write coalesced runs ----
-    u32 pos[SORT_ITEMS];
+    // ---- scatter keys and values to their locally sorted position, then write coalesced runs ----
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         int loc = wbase + i * 32;
         u32 d = (loc < nvalid) ? ((key[i] >> shift) & mask) : (u32)(RADIX - 1);
-        pos[i] = s_local[d] + wc[d] + rank[i];
-        s_buf[pos[i]] = key[i];
+        u32 pos = s_local[d] + wc[d] + rank[i];
+        u32 v = 0;
+        if (loc < nvalid) v = IOTA ? (u32)(tile_base + loc) : vals_in[tile_base + loc];
+        s_keys[pos] = key[i];
+        s_vals[pos] = v;
     }
     __syncthreads();
-    u32 dst[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         int p = i * SORT_THREADS + tid;
         if (p < nvalid) {
-            u32 k = s_buf[p];
+            u32 k = s_keys[p];
             u32 d = (k >> shift) & mask;
-            dst[i] = s_gbase[d] + (u32)p;
-            keys_out[dst[i]] = k;
+            u32 dst = s_gbase[d] + (u32)p;
+            keys_out[dst] = k;
+            vals_out[dst] = s_vals[p];
         }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++) {
-        int loc = wbase + i * 32;
-        u32 v = 0;
-        if (loc < nvalid) v = IOTA ? (u32)(tile_base + loc) : vals_in[tile_base + loc];
-        s_buf[pos[i]] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++) {
-        int p = i * SORT_THREADS + tid;
-        if (p < nvalid) vals_out[dst[i]] = s_buf[p];
     }
 }
 
@@ -253,12 +281,19 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
 }
 
 // =================================================================================================================
-// Emit (tile, id) instances in depth order; output offsets by a chained (decoupled look-back) scan in the same kernel.
+// Emit (tile, id) instances in depth order, in two load-balanced steps:
+//   scan : exclusive prefix sum of the tile counts in depth order (chained / decoupled look-back scan over CTAs of
+//          EMIT_THREADS Gaussians) -> offsets[i] = first output slot of the i-th Gaussian in depth order;
+//   fill : one thread per OUTPUT slot.  A CTA owns EMIT_FILL_SLOTS consecutive slots, finds the first Gaussian of its
+//          range with a warp-wide 32-ary search over `offsets`, stages that window of offsets in shared memory and
+//          binary-searches it per slot.  Near Gaussians cover hundreds of tiles and far ones a single tile; filling
+//          by slot instead of by Gaussian removes that skew (the per-Gaussian version spent most of its time in the
+//          first CTAs' tails) and makes every store fully coalesced.
 // =================================================================================================================
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_instances_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect, int grid_x,
-                      unsigned long long* __restrict__ counters, u32* __restrict__ emit_status,
-                      u32* __restrict__ tile_out, u32* __restrict__ id_out) {
+emit_scan_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect,
+                 unsigned long long* __restrict__ counters, u32* __restrict__ emit_status,
+                 u32* __restrict__ offsets) {
     __shared__ u32 s_wsum[EMIT_THREADS / 32];
     __shared__ u32 s_tile;
     __shared__ u32 s_base;
@@ -268,13 +303,11 @@ emit_instances_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* 
     const u32 tile = s_tile;
     const int i = tile * EMIT_THREADS + tid;
 
-    u32 g = 0;
-    ushort4 r = make_ushort4(0, 0, 0, 0);
+    u32 cnt = 0;
     if (i < P) {
-        g = sorted_idx[i];
-        r = rect[g];
+        const ushort4 r = rect[sorted_idx[i]];
+        cnt = (u32)r.z * (u32)r.w;
     }
-    const u32 cnt = (u32)r.z * (u32)r.w;
 
     // warp inclusive scan of counts
     u32 inc = cnt;
@@ -292,98 +325,163 @@ emit_instances_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* 
         if (k < warp) wbase += v;
         total += v;
     }
-    // chained scan across CTAs (one word: 2 flag bits + 30 value bits)
-    if (tid == 0) {
+    // chained scan across CTAs (one word: 2 flag bits + 30 value bits).  Warp 0 looks back 64 predecessors per round.
+    if (warp == 0) {
         u32 excl = 0;
         if (tile > 0) {
-            st_volatile_u32(&emit_status[tile], total | FLAG_AGG);
+            if (lane == 0) st_volatile_u32(&emit_status[tile], total | FLAG_AGG);
             int look = (int)tile - 1;
             while (true) {
-                u32 s = ld_volatile_u32(&emit_status[look]);
-                u32 f = s & ~VAL_MASK;
-                if (f == 0) continue;
-                excl += s & VAL_MASK;
-                if (f == FLAG_INCL) break;
-                look--;
+                // lane l reads tiles look-l and look-32-l (independent loads)
+                const int t0 = look - lane, t1 = look - 32 - lane;
+                u32 s0 = FLAG_INCL, s1 = FLAG_INCL;       // before tile 0: inclusive prefix 0
+                if (t0 >= 0) s0 = ld_volatile_u32(&emit_status[t0]);
+                if (t1 >= 0) s1 = ld_volatile_u32(&emit_status[t1]);
+                while ((s0 & ~VAL_MASK) == 0) s0 = ld_volatile_u32(&emit_status[t0]);
+                const u32 incl0 = __ballot_sync(0xffffffffu, (s0 & ~VAL_MASK) == FLAG_INCL);
+                u32 v;
+                bool found = incl0 != 0;
+                if (found) {
+                    // nearest predecessor holding an inclusive prefix is in the first half of the window
+                    v = (lane <= __ffs(incl0) - 1) ? (s0 & VAL_MASK) : 0u;
+                } else {
+                    while ((s1 & ~VAL_MASK) == 0) s1 = ld_volatile_u32(&emit_status[t1]);
+                    const u32 incl1 = __ballot_sync(0xffffffffu, (s1 & ~VAL_MASK) == FLAG_INCL);
+                    found = incl1 != 0;
+                    const int first = found ? __ffs(incl1) - 1 : 31;
+                    v = (s0 & VAL_MASK) + ((lane <= first) ? (s1 & VAL_MASK) : 0u);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (found) break;
+                look -= 64;
             }
         }
-        st_volatile_u32(&emit_status[tile], ((excl + total) & VAL_MASK) | FLAG_INCL);
-        s_base = excl;
+        if (lane == 0) {
+            st_volatile_u32(&emit_status[tile], ((excl + total) & VAL_MASK) | FLAG_INCL);
+            s_base = excl;
+        }
     }
     __syncthreads();
-    const u32 start = s_base + wbase + inc - cnt;  // first output slot of this lane's Gaussian
+    if (i < P) offsets[i] = s_base + wbase + inc - cnt;
+}
 
-    // warp-cooperative, coalesced emission: slot s of the warp's contiguous output range belongs to the lane whose
-    // [start, start+cnt) contains it.
-    const u32 wstart = __shfl_sync(0xffffffffu, start, 0);
-    const u32 wtotal = __shfl_sync(0xffffffffu, inc, 31);
-    const u32 packed_min = (u32)r.x | ((u32)r.y << 16);
-    const u32 width = r.z;
-    // NB: the loop trip count is warp-uniform; every lane takes part in the shuffles and only the stores are guarded.
-    for (u32 sbase = 0; sbase < wtotal; sbase += 32) {
-        const u32 s = sbase + lane;
-        const bool active = s < wtotal;
-        const u32 slot = wstart + (active ? s : 0u);
-        // largest lane k with start_k <= slot (starts are non-decreasing)
-        int lo = 0;
+constexpr int EMIT_FILL_THREADS = 256;
+constexpr int EMIT_FILL_ITEMS = 8;
+constexpr int EMIT_FILL_SLOTS = EMIT_FILL_THREADS * EMIT_FILL_ITEMS;   // output slots per CTA
+constexpr int EMIT_FILL_WINDOW = EMIT_FILL_SLOTS + 1;                  // staged offsets (owners of 2048 slots when
+                                                                       // every Gaussian has >= 1 tile)
+
+__global__ void __launch_bounds__(EMIT_FILL_THREADS)
+emit_fill_kernel(int P, u32 R, const u32* __restrict__ offsets, const u32* __restrict__ sorted_idx,
+                 const ushort4* __restrict__ rect, int grid_x, u32* __restrict__ tile_out, u32* __restrict__ id_out) {
+    __shared__ u32 s_off[EMIT_FILL_WINDOW];
+    __shared__ int s_lo;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 slot0 = blockIdx.x * (u32)EMIT_FILL_SLOTS;
+
+    // first Gaussian (in depth order) of this CTA's range: the last i with offsets[i] <= slot0
+    if (tid < 32) {
+        int lo = 0, hi = P;   // offsets[lo] <= slot0 (offsets[0] == 0); the answer lies in [lo, hi)
+        while (hi - lo > 1) {
+            const int step = (hi - lo + 31) >> 5;
+            const int p = lo + lane * step;
+            const bool le = (p < hi) && (offsets[p] <= slot0);
+            const int c = __popc(__ballot_sync(0xffffffffu, le));   // offsets are non-decreasing: a prefix of lanes
+            lo += (c - 1) * step;
+            hi = min(lo + step, hi);
+        }
+        if (lane == 0) s_lo = lo;
+    }
+    __syncthreads();
+    const int i_lo = s_lo;
+    const int nwin = min(EMIT_FILL_WINDOW, P - i_lo);
+    for (int k = tid; k < nwin; k += EMIT_FILL_THREADS) s_off[k] = offsets[i_lo + k];
+    __syncthreads();
+
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int cand = lo + step;   // <= 31
-            const u32 sk = __shfl_sync(0xffffffffu, start, cand);
-            if (sk <= slot) lo = cand;
+    for (int it = 0; it < EMIT_FILL_ITEMS; it++) {
+        const u32 slot = slot0 + (u32)(it * EMIT_FILL_THREADS + tid);
+        if (slot >= R) break;
+        // last j in the window with s_off[j] <= slot
+        int lo = 0, hi = nwin;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= slot) lo = mid; else hi = mid;
         }
-        // zero-count lanes share their start with the next lane; the search lands on the last lane of such a run,
-        // which is the non-empty owner because slot < wstart + wtotal.
-        const u32 ostart = __shfl_sync(0xffffffffu, start, lo);
-        const u32 omin = __shfl_sync(0xffffffffu, packed_min, lo);
-        const u32 ow = __shfl_sync(0xffffffffu, width, lo);
-        const u32 og = __shfl_sync(0xffffffffu, g, lo);
-        if (active) {
-            const u32 local = slot - ostart;
-            const u32 ty = (omin >> 16) + local / ow;
-            const u32 tx = (omin & 0xFFFFu) + local % ow;
-            tile_out[slot] = ty * (u32)grid_x + tx;
-            id_out[slot] = og;
+        int i = i_lo + lo;
+        u32 start = s_off[lo];
+        if (lo == nwin - 1 && i + 1 < P && offsets[i + 1] <= slot) {
+            // more than EMIT_FILL_SLOTS Gaussians share this CTA's range (zero-count entries inside the list):
+            // finish the search in global memory
+            int glo = i + 1, ghi = P;
+            while (ghi - glo > 1) {
+                const int mid = (glo + ghi) >> 1;
+                if (offsets[mid] <= slot) glo = mid; else ghi = mid;
+            }
+            i = glo;
+            start = offsets[glo];
         }
+        const u32 g = sorted_idx[i];
+        const ushort4 r = rect[g];
+        const u32 local = slot - start;
+        const u32 ty = (u32)r.y + local / (u32)r.z;
+        const u32 tx = (u32)r.x + local % (u32)r.z;
+        tile_out[slot] = ty * (u32)grid_x + tx;
+        id_out[slot] = g;
     }
 }
 
-int launch_emit(int P, const GeomState& g, const u32* sorted_idx, BinningState& b, int grid_x, cudaStream_t st) {
+int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st) {
     const int blocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;
-    emit_instances_kernel<<<blocks, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, grid_x, g.counters,
-                                                          g.emit_status, b.tile_buf[0], b.id_buf[0]);
-    BAGS_LAUNCH_OK("emit_instances_kernel");
+    emit_scan_kernel<<<blocks, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.counters, g.emit_status, offsets);
+    BAGS_LAUNCH_OK("emit_scan_kernel");
+    return 0;
+}
+
+int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, const u32* offsets, BinningState& b,
+                     int grid_x, cudaStream_t st) {
+    const int blocks = (R + EMIT_FILL_SLOTS - 1) / EMIT_FILL_SLOTS;
+    emit_fill_kernel<<<blocks, EMIT_FILL_THREADS, 0, st>>>(P, (u32)R, offsets, sorted_idx, g.rect, grid_x,
+                                                          b.tile_buf[0], b.id_buf[0]);
+    BAGS_LAUNCH_OK("emit_fill_kernel");
     return 0;
 }
 
 // =================================================================================================================
-// Tile ranges by binary search over the sorted tile ids.
+// Tile ranges from the boundaries of the sorted tile ids (identifyTileRanges, rasterizer_impl.cu:116-138).
+// Untouched tiles keep the (0,0) of the memset, like the reference's cudaMemset.
 // =================================================================================================================
-__device__ __forceinline__ u32 lower_bound_u32(const u32* __restrict__ a, u32 n, u32 key) {
-    u32 lo = 0, hi = n;
-    while (lo < hi) {
-        u32 mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
+constexpr int RANGE_ITEMS = 4;
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(int R, const u32* __restrict__ tile_sorted, uint2* __restrict__ ranges) {
+    // thread-striped over RANGE_ITEMS * 256 consecutive elements per CTA (coalesced loads)
+    const int base = blockIdx.x * (256 * RANGE_ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < RANGE_ITEMS; k++) {
+        const int i = base + k * 256;
+        if (i >= R) break;
+        const u32 t = tile_sorted[i];
+        if (i == 0) {
+            ranges[t].x = 0;
+        } else {
+            const u32 prev = tile_sorted[i - 1];
+            if (t != prev) {
+                ranges[prev].y = (u32)i;
+                ranges[t].x = (u32)i;
+            }
+        }
+        if (i == R - 1) ranges[t].y = (u32)R;
     }
-    return lo;
-}
-
-__global__ void tile_ranges_kernel(int R, int ntiles, const u32* __restrict__ tile_sorted,
-                                   uint2* __restrict__ ranges) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    u32 lo = 0, hi = 0;
-    if (R > 0) {
-        lo = lower_bound_u32(tile_sorted, (u32)R, (u32)t);
-        hi = lower_bound_u32(tile_sorted, (u32)R, (u32)t + 1u);
-    }
-    if (lo == hi) { lo = 0; hi = 0; }   // untouched tiles keep the reference's memset value
-    ranges[t] = make_uint2(lo, hi);
 }
 
 int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st) {
-    tile_ranges_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(R, ntiles, tile_sorted, ranges);
-    BAGS_LAUNCH_OK("tile_ranges_kernel");
+    BAGS_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)ntiles * sizeof(uint2), st));
+    if (R > 0) {
+        tile_ranges_kernel<<<(R + 256 * RANGE_ITEMS - 1) / (256 * RANGE_ITEMS), 256, 0, st>>>(R, tile_sorted, ranges);
+        BAGS_LAUNCH_OK("tile_ranges_kernel");
+    }
     return 0;
 }
 

@@ -317,33 +317,47 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     const size_t plane = (size_t)H * W;
     const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
-    // per-pixel state (registers; every loop over k is fully unrolled)
-    float pyf[PPT], T[PPT], ar0[PPT], ar1[PPT], ar2[PPT], ad[PPT], aa[PPT];
-    float g0[PPT], g1[PPT], g2[PPT], gd[PPT], gw[PPT], nTbg[PPT];
+    // Per-pixel state (registers; every loop over k is fully unrolled).  The pixel's upstream gradients are
+    // loop-invariant: with 4 pixels per thread they live in shared memory (two conflict-free loads per evaluated
+    // pixel) to keep the kernel under 96 registers; with 1 or 2 they stay in registers.
+    constexpr bool G_IN_SMEM = PPT >= 4;
+    __shared__ __align__(16) float4 sm_g[G_IN_SMEM ? 256 : 1];   // {dL_dR, dL_dG, dL_dB, dL_ddepth}
+    __shared__ __align__(8) float2 sm_w[G_IN_SMEM ? 256 : 1];    // {dL_dweight, -T_final * (bg . dL_dcolour)}
+    const u32 s_g = smem_addr(sm_g), s_w = smem_addr(sm_w);
+    const float pyf0 = (float)(blockIdx.y * TILE_Y + wp.ly(lane, 0));   // row of pixel k is pyf0 + 4k (exact)
+    float T[PPT], ar0[PPT], ar1[PPT], ar2[PPT], ad[PPT], aa[PPT];
+    float g0[G_IN_SMEM ? 1 : PPT], g1[G_IN_SMEM ? 1 : PPT], g2[G_IN_SMEM ? 1 : PPT], gd[G_IN_SMEM ? 1 : PPT],
+        gw[G_IN_SMEM ? 1 : PPT], nTbg[G_IN_SMEM ? 1 : PPT];
     u32 last_contributor[PPT], pmax[PPT];
     u32 warp_max = 0;
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
         const u32 py = blockIdx.y * TILE_Y + wp.ly(lane, k);
-        pyf[k] = (float)py;
         const bool inside = px < (u32)W && py < (u32)H;
         const u32 pix_id = (u32)W * py + px;
         const float T_final = inside ? final_Ts[pix_id] : 0;
         T[k] = T_final;
         last_contributor[k] = inside ? n_contrib[pix_id] : 0;
-        g0[k] = g1[k] = g2[k] = gd[k] = gw[k] = 0.f;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w = 0.f;
         if (inside) {
-            g0[k] = dL_dpixels[0 * plane + pix_id];
-            g1[k] = dL_dpixels[1 * plane + pix_id];
-            g2[k] = dL_dpixels[2 * plane + pix_id];
-            gd[k] = dL_dpixel_depths[pix_id];
-            gw[k] = dL_dalphas[pix_id];
+            g.x = dL_dpixels[0 * plane + pix_id];
+            g.y = dL_dpixels[1 * plane + pix_id];
+            g.z = dL_dpixels[2 * plane + pix_id];
+            g.w = dL_dpixel_depths[pix_id];
+            w = dL_dalphas[pix_id];
         }
         float bg_dot_dpixel = 0;
-        bg_dot_dpixel += bg0 * g0[k];
-        bg_dot_dpixel += bg1 * g1[k];
-        bg_dot_dpixel += bg2 * g2[k];
-        nTbg[k] = -T_final * bg_dot_dpixel;
+        bg_dot_dpixel += bg0 * g.x;
+        bg_dot_dpixel += bg1 * g.y;
+        bg_dot_dpixel += bg2 * g.z;
+        const float ntb = -T_final * bg_dot_dpixel;
+        if (G_IN_SMEM) {
+            sm_g[k * NT + tid] = g;
+            sm_w[k * NT + tid] = make_float2(w, ntb);
+        } else {
+            g0[k] = g.x; g1[k] = g.y; g2[k] = g.z; gd[k] = g.w; gw[k] = w; nTbg[k] = ntb;
+        }
         ar0[k] = ar1[k] = ar2[k] = ad[k] = aa[k] = 0.f;
         // Only list positions below the largest n_contrib of the patch / warp / CTA can contribute.
         pmax[k] = __reduce_max_sync(FULL, last_contributor[k]);
@@ -393,13 +407,22 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                 for (int k = 0; k < PPT; k++) {
                     // warp-uniform: does the splat's box reach this patch, and is the position still live there?
                     if (((cm >> wp.cell_shift(k)) & 0x33u) == 0u || pos >= pmax[k]) continue;
-                    const float2 d = {dx, q0.y - pyf[k]};
+                    const float2 d = {dx, q0.y - (pyf0 + (float)(4 * k))};
                     const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
                     const float Gv = exp(power);
                     const float alpha = min(0.99f, con_o.w * Gv);
                     const bool valid = (pos < last_contributor[k]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                     if (!valid) continue;
                     any_valid = true;
+                    float G0, G1, G2, GD, GW, NTBG;
+                    if (G_IN_SMEM) {
+                        const float4 g = lds128(s_g + (k * NT + tid) * 16);
+                        float2 w;
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(w.x), "=f"(w.y) : "r"(s_w + (k * NT + tid) * 8));
+                        G0 = g.x; G1 = g.y; G2 = g.z; GD = g.w; GW = w.x; NTBG = w.y;
+                    } else {
+                        G0 = g0[k]; G1 = g1[k]; G2 = g2[k]; GD = gd[k]; GW = gw[k]; NTBG = nTbg[k];
+                    }
                     // T_j = T_{j+1} / (1 - alpha); one reciprocal serves both divisions of backward.cu:1051,1090
                     const float rcp = __fdividef(1.0f, 1.f - alpha);
                     T[k] = T[k] * rcp;
@@ -408,23 +431,23 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                     const float one_minus_alpha = 1.f - alpha;
                     float dL_dalpha = 0.0f;
                     // ar* hold "colour behind this splat" (the reference's accum_rec after its update)
-                    dL_dalpha += (col.x - ar0[k]) * g0[k];
-                    dL_dalpha += (col.y - ar1[k]) * g1[k];
-                    dL_dalpha += (col.z - ar2[k]) * g2[k];
-                    v[GA_R] += dchannel_dcolor * g0[k];
-                    v[GA_G] += dchannel_dcolor * g1[k];
-                    v[GA_B] += dchannel_dcolor * g2[k];
+                    dL_dalpha += (col.x - ar0[k]) * G0;
+                    dL_dalpha += (col.y - ar1[k]) * G1;
+                    dL_dalpha += (col.z - ar2[k]) * G2;
+                    v[GA_R] += dchannel_dcolor * G0;
+                    v[GA_G] += dchannel_dcolor * G1;
+                    v[GA_B] += dchannel_dcolor * G2;
                     ar0[k] = alpha * col.x + one_minus_alpha * ar0[k];
                     ar1[k] = alpha * col.y + one_minus_alpha * ar1[k];
                     ar2[k] = alpha * col.z + one_minus_alpha * ar2[k];
-                    dL_dalpha += (q0.z - ad[k]) * gd[k];
-                    v[GA_DEPTH] += dchannel_dcolor * gd[k];
+                    dL_dalpha += (q0.z - ad[k]) * GD;
+                    v[GA_DEPTH] += dchannel_dcolor * GD;
                     ad[k] = alpha * q0.z + one_minus_alpha * ad[k];
-                    dL_dalpha += (1 - aa[k]) * gw[k];
+                    dL_dalpha += (1 - aa[k]) * GW;
                     aa[k] = alpha + one_minus_alpha * aa[k];
 
                     dL_dalpha *= T[k];
-                    dL_dalpha += nTbg[k] * rcp;
+                    dL_dalpha += NTBG * rcp;
 
                     const float dL_dG = con_o.w * dL_dalpha;
                     const float gdx = Gv * d.x;

@@ -56,9 +56,9 @@ inline void carve(char*& p, T*& out, size_t count) {
 }
 
 // Radix-sort bookkeeping shared by the depth sort (P items) and the tile sort (R items).
-constexpr int SORT_THREADS = 512;
+constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 8192 keys per CTA
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
@@ -108,7 +108,7 @@ struct GeomState {
     static GeomState from(char* p, int P);
 };
 
-constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_THREADS = 1024;  // Gaussians per emit CTA (= per chained-scan tile)
 
 // Tile-sort ping-pong: emit fills (tile_buf[0], id_buf[0]); after `npass` passes the sorted data is in buffer npass&1.
 struct BinningState {
@@ -166,7 +166,9 @@ int launch_unpack(int P, int R, int W, int H, const GeomState& g, const BinningS
                   u64* point_list_keys, u32* ranges, u32* n_contrib, float* final_T, cudaStream_t st);
 int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* vals_out, int begin_bit, int end_bit,
                       SortScratch& sc, bool iota_vals, cudaStream_t st, u32** final_keys, u32** final_vals);
-int launch_emit(int P, const GeomState& g, const u32* sorted_idx, BinningState& b, int grid_x, cudaStream_t st);
+int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st);
+int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, const u32* offsets, BinningState& b,
+                     int grid_x, cudaStream_t st);
 int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st);
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);

@@ -78,7 +78,7 @@ def main():
         torch.cuda.synchronize()
         wall = (time.time() - t0) / (3 * len(views)) * 1e3
         dev_ms = e0.elapsed_time(e1) / (3 * len(views))
-        out = {k: round(ms[k] / max(calls[k], 1), 4) for k in ms}
+        out = {k: round(ms[k] / max(calls["preprocess"], 1), 4) for k in ms}
         print(json.dumps({"ppt_fwd:bwd": G, "P": P, "V": V, "R": R, "scale": a.scale, "stage_ms": out,
                           "sum_ms": round(sum(out.values()), 4), "ms_per_view_events": round(dev_ms, 4),
                           "ms_per_view_wall": round(wall, 4)}))
