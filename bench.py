@@ -7,8 +7,8 @@ Contract (see DESIGN.md "Measurement"): a step = one training iteration over `vi
 (weak scaling): every view is rendered forward and back-propagated through the public GaussianRasterizer API, the
 Gaussian-parameter gradients accumulate in one flat buffer and (N>1) are summed with one NCCL all-reduce.
 `value` = views/s with the upstream image gradients resident in HBM; `e2e` = the same through host buffers: each
-view's ground-truth image comes from pinned host memory (H2D), the L1 loss is computed on the device and read back
-(D2H) inside the timed region.  Prints ONE JSON line on rank 0.
+view's ground-truth image comes from pinned host memory (H2D on a copy stream, prefetched one view ahead), the L1 loss
+is computed on the device and read back (D2H) inside the timed region.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -227,15 +227,36 @@ def main():
         if use_dist:
             VP.allreduce_gradients(params)
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def issue_h2d(vw):
+        """host->device copy of one view's ground truth on the copy stream (after the previous reader of the buffer)"""
+        with torch.cuda.stream(copy_stream):
+            if vw.get("used_ev") is not None:
+                copy_stream.wait_event(vw["used_ev"])
+            vw["gt_dev"].copy_(vw["gt_host"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
     def step_e2e():
-        """ground-truth image from pinned host memory, L1 loss read back"""
+        """ground-truth image from pinned host memory (H2D every view, prefetched one view ahead on a copy stream so
+        that it overlaps the previous view's kernels), L1 loss on the device, loss read back"""
         params.zero_grad()
         total = None
-        for vw in views:
-            vw["gt_dev"].copy_(vw["gt_host"], non_blocking=True)
+        main = torch.cuda.current_stream()
+        ev_next = issue_h2d(views[0])
+        for k, vw in enumerate(views):
+            ev = ev_next
+            if k + 1 < len(views):
+                ev_next = issue_h2d(views[k + 1])
             color, radii, depth, weights, _ = render(vw)
+            main.wait_event(ev)
             loss = (color - vw["gt_dev"]).abs().mean()
             loss.backward()
+            used = torch.cuda.Event()
+            used.record(main)
+            vw["used_ev"] = used
             total = loss.detach() if total is None else total + loss.detach()
         if use_dist:
             VP.allreduce_gradients(params)
