@@ -8,7 +8,7 @@
 //   1. depth sort   : stable sort of the P Gaussians by their 32 depth bits (culled ones carry 0xFFFFFFFF),
 //                     4 x 8-bit onesweep passes over P x 8 B  -> order (depth, id);
 //   2. emit         : in that order, append (tile, id) for every tile of the stored rectangle (y outer, x inner
-//                     like rasterizer_impl.cu:98-108): a decoupled look-back scan of the tile counts, then a
+//                     like rasterizer_impl.cu:98-108): a two-launch scan of the tile counts, then a
 //                     slot-parallel fill (one thread per output instance);
 //   3. tile sort    : stable sort of the R instances by tile id only, ceil(bit/8) (= 2) passes over R x 8 B
 //                     -> order (tile, depth, id), identical to the reference's point_list;
@@ -282,32 +282,57 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
 
 // =================================================================================================================
 // Emit (tile, id) instances in depth order, in two load-balanced steps:
-//   scan : exclusive prefix sum of the tile counts in depth order (chained / decoupled look-back scan over CTAs of
-//          EMIT_THREADS Gaussians) -> offsets[i] = first output slot of the i-th Gaussian in depth order;
+//   scan : exclusive prefix sum of the tile counts in depth order (per-CTA totals, then every CTA adds up the totals
+//          before it) -> offsets[i] = first output slot of the i-th Gaussian in depth order;
 //   fill : one thread per OUTPUT slot.  A CTA owns EMIT_FILL_SLOTS consecutive slots, finds the first Gaussian of its
 //          range with a warp-wide 32-ary search over `offsets`, stages that window of offsets in shared memory and
 //          binary-searches it per slot.  Near Gaussians cover hundreds of tiles and far ones a single tile; filling
 //          by slot instead of by Gaussian removes that skew (the per-Gaussian version spent most of its time in the
 //          first CTAs' tails) and makes every store fully coalesced.
 // =================================================================================================================
+// count: per-CTA totals (no inter-CTA dependency).  scan: every CTA sums the totals of the CTAs before it (a block
+// reduction over at most a few thousand words) and scans its own counts -- two short launches instead of a chained
+// look-back, whose CTAs spent most of their life spinning on their predecessors' flags.
+__device__ __forceinline__ u32 emit_count_of(int i, int P, const u32* __restrict__ sorted_idx,
+                                             const ushort4* __restrict__ rect) {
+    if (i >= P) return 0u;
+    const ushort4 r = rect[sorted_idx[i]];
+    return (u32)r.z * (u32)r.w;
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_count_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect,
+                  u32* __restrict__ tile_total) {
+    __shared__ u32 s_wsum[EMIT_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 v = emit_count_of(blockIdx.x * EMIT_THREADS + tid, P, sorted_idx, rect);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        u32 t = s_wsum[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) tile_total[blockIdx.x] = t;
+    }
+}
+
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_scan_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect,
-                 unsigned long long* __restrict__ counters, u32* __restrict__ emit_status,
-                 u32* __restrict__ offsets) {
+                 const u32* __restrict__ tile_total, u32* __restrict__ offsets) {
     __shared__ u32 s_wsum[EMIT_THREADS / 32];
-    __shared__ u32 s_tile;
-    __shared__ u32 s_base;
+    __shared__ u32 s_wbase[EMIT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = (u32)atomicAdd(&counters[1], 1ull);
-    __syncthreads();
-    const u32 tile = s_tile;
-    const int i = tile * EMIT_THREADS + tid;
+    const int i = blockIdx.x * EMIT_THREADS + tid;
+    const u32 cnt = emit_count_of(i, P, sorted_idx, rect);
 
-    u32 cnt = 0;
-    if (i < P) {
-        const ushort4 r = rect[sorted_idx[i]];
-        cnt = (u32)r.z * (u32)r.w;
-    }
+    // sum of the totals of all CTAs before this one
+    u32 before = 0;
+    for (int j = tid; j < (int)blockIdx.x; j += EMIT_THREADS) before += tile_total[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) s_wbase[warp] = before;
 
     // warp inclusive scan of counts
     u32 inc = cnt;
@@ -318,53 +343,15 @@ emit_scan_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __res
     }
     if (lane == 31) s_wsum[warp] = inc;
     __syncthreads();
-    u32 wbase = 0, total = 0;
+    // lane k of every warp holds warp k's total / partial base: one more shuffle reduction gives this warp's offset
+    u32 wsum = s_wsum[lane], base = s_wbase[lane];
+    u32 wbase = (lane < warp) ? wsum : 0u;
 #pragma unroll
-    for (int k = 0; k < EMIT_THREADS / 32; k++) {
-        u32 v = s_wsum[k];
-        if (k < warp) wbase += v;
-        total += v;
+    for (int o = 16; o > 0; o >>= 1) {
+        wbase += __shfl_xor_sync(0xffffffffu, wbase, o);
+        base += __shfl_xor_sync(0xffffffffu, base, o);
     }
-    // chained scan across CTAs (one word: 2 flag bits + 30 value bits).  Warp 0 looks back 64 predecessors per round.
-    if (warp == 0) {
-        u32 excl = 0;
-        if (tile > 0) {
-            if (lane == 0) st_volatile_u32(&emit_status[tile], total | FLAG_AGG);
-            int look = (int)tile - 1;
-            while (true) {
-                // lane l reads tiles look-l and look-32-l (independent loads)
-                const int t0 = look - lane, t1 = look - 32 - lane;
-                u32 s0 = FLAG_INCL, s1 = FLAG_INCL;       // before tile 0: inclusive prefix 0
-                if (t0 >= 0) s0 = ld_volatile_u32(&emit_status[t0]);
-                if (t1 >= 0) s1 = ld_volatile_u32(&emit_status[t1]);
-                while ((s0 & ~VAL_MASK) == 0) s0 = ld_volatile_u32(&emit_status[t0]);
-                const u32 incl0 = __ballot_sync(0xffffffffu, (s0 & ~VAL_MASK) == FLAG_INCL);
-                u32 v;
-                bool found = incl0 != 0;
-                if (found) {
-                    // nearest predecessor holding an inclusive prefix is in the first half of the window
-                    v = (lane <= __ffs(incl0) - 1) ? (s0 & VAL_MASK) : 0u;
-                } else {
-                    while ((s1 & ~VAL_MASK) == 0) s1 = ld_volatile_u32(&emit_status[t1]);
-                    const u32 incl1 = __ballot_sync(0xffffffffu, (s1 & ~VAL_MASK) == FLAG_INCL);
-                    found = incl1 != 0;
-                    const int first = found ? __ffs(incl1) - 1 : 31;
-                    v = (s0 & VAL_MASK) + ((lane <= first) ? (s1 & VAL_MASK) : 0u);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
-                if (found) break;
-                look -= 64;
-            }
-        }
-        if (lane == 0) {
-            st_volatile_u32(&emit_status[tile], ((excl + total) & VAL_MASK) | FLAG_INCL);
-            s_base = excl;
-        }
-    }
-    __syncthreads();
-    if (i < P) offsets[i] = s_base + wbase + inc - cnt;
+    if (i < P) offsets[i] = base + wbase + inc - cnt;
 }
 
 constexpr int EMIT_FILL_THREADS = 256;
@@ -372,11 +359,12 @@ constexpr int EMIT_FILL_ITEMS = 8;
 constexpr int EMIT_FILL_SLOTS = EMIT_FILL_THREADS * EMIT_FILL_ITEMS;   // output slots per CTA
 constexpr int EMIT_FILL_WINDOW = EMIT_FILL_SLOTS + 1;                  // staged offsets (owners of 2048 slots when
                                                                        // every Gaussian has >= 1 tile)
+constexpr int EMIT_FILL_PAD = 2 * EMIT_FILL_SLOTS;                     // power-of-two search array (sentinel padded)
 
 __global__ void __launch_bounds__(EMIT_FILL_THREADS)
 emit_fill_kernel(int P, u32 R, const u32* __restrict__ offsets, const u32* __restrict__ sorted_idx,
                  const ushort4* __restrict__ rect, int grid_x, u32* __restrict__ tile_out, u32* __restrict__ id_out) {
-    __shared__ u32 s_off[EMIT_FILL_WINDOW];
+    __shared__ u32 s_off[EMIT_FILL_PAD];
     __shared__ int s_lo;
     const int tid = threadIdx.x, lane = tid & 31;
     const u32 slot0 = blockIdx.x * (u32)EMIT_FILL_SLOTS;
@@ -397,45 +385,62 @@ emit_fill_kernel(int P, u32 R, const u32* __restrict__ offsets, const u32* __res
     __syncthreads();
     const int i_lo = s_lo;
     const int nwin = min(EMIT_FILL_WINDOW, P - i_lo);
-    for (int k = tid; k < nwin; k += EMIT_FILL_THREADS) s_off[k] = offsets[i_lo + k];
+    for (int k = tid; k < EMIT_FILL_PAD; k += EMIT_FILL_THREADS) s_off[k] = (k < nwin) ? offsets[i_lo + k] : 0xFFFFFFFFu;
     __syncthreads();
 
+    // All EMIT_FILL_ITEMS slots of a thread advance together (branch-free binary search, then the two dependent
+    // gathers), so their shared-memory and global latencies overlap.
+    u32 slot[EMIT_FILL_ITEMS];
+    int own[EMIT_FILL_ITEMS];
 #pragma unroll
     for (int it = 0; it < EMIT_FILL_ITEMS; it++) {
-        const u32 slot = slot0 + (u32)(it * EMIT_FILL_THREADS + tid);
-        if (slot >= R) break;
-        // last j in the window with s_off[j] <= slot
-        int lo = 0, hi = nwin;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= slot) lo = mid; else hi = mid;
-        }
-        int i = i_lo + lo;
-        u32 start = s_off[lo];
-        if (lo == nwin - 1 && i + 1 < P && offsets[i + 1] <= slot) {
+        slot[it] = slot0 + (u32)(it * EMIT_FILL_THREADS + tid);
+        own[it] = 0;
+    }
+#pragma unroll
+    for (int step = EMIT_FILL_PAD / 2; step > 0; step >>= 1) {
+#pragma unroll
+        for (int it = 0; it < EMIT_FILL_ITEMS; it++)
+            if (s_off[own[it] + step] <= slot[it]) own[it] += step;   // last j with s_off[j] <= slot (s_off[0] <= slot0)
+    }
+    u32 start[EMIT_FILL_ITEMS], g[EMIT_FILL_ITEMS];
+#pragma unroll
+    for (int it = 0; it < EMIT_FILL_ITEMS; it++) {
+        int i = i_lo + own[it];
+        start[it] = s_off[own[it]];
+        if (slot[it] < R && own[it] == nwin - 1 && i + 1 < P && offsets[i + 1] <= slot[it]) {
             // more than EMIT_FILL_SLOTS Gaussians share this CTA's range (zero-count entries inside the list):
             // finish the search in global memory
             int glo = i + 1, ghi = P;
             while (ghi - glo > 1) {
                 const int mid = (glo + ghi) >> 1;
-                if (offsets[mid] <= slot) glo = mid; else ghi = mid;
+                if (offsets[mid] <= slot[it]) glo = mid; else ghi = mid;
             }
             i = glo;
-            start = offsets[glo];
+            start[it] = offsets[glo];
         }
-        const u32 g = sorted_idx[i];
-        const ushort4 r = rect[g];
-        const u32 local = slot - start;
-        const u32 ty = (u32)r.y + local / (u32)r.z;
-        const u32 tx = (u32)r.x + local % (u32)r.z;
-        tile_out[slot] = ty * (u32)grid_x + tx;
-        id_out[slot] = g;
+        g[it] = (slot[it] < R) ? sorted_idx[i] : 0u;
+    }
+    ushort4 r[EMIT_FILL_ITEMS];
+#pragma unroll
+    for (int it = 0; it < EMIT_FILL_ITEMS; it++) r[it] = rect[g[it]];
+#pragma unroll
+    for (int it = 0; it < EMIT_FILL_ITEMS; it++) {
+        if (slot[it] >= R) continue;
+        const u32 local = slot[it] - start[it];
+        const u32 w = max((u32)r[it].z, 1u);
+        const u32 ty = (u32)r[it].y + local / w;
+        const u32 tx = (u32)r[it].x + local % w;
+        tile_out[slot[it]] = ty * (u32)grid_x + tx;
+        id_out[slot[it]] = g[it];
     }
 }
 
 int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st) {
     const int blocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;
-    emit_scan_kernel<<<blocks, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.counters, g.emit_status, offsets);
+    emit_count_kernel<<<blocks, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.emit_status);
+    BAGS_LAUNCH_OK("emit_count_kernel");
+    emit_scan_kernel<<<blocks, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.emit_status, offsets);
     BAGS_LAUNCH_OK("emit_scan_kernel");
     return 0;
 }

@@ -101,8 +101,8 @@ struct GeomState {
     u32* key_b;        // [P]
     u32* idx_a;        // [P] Gaussian ids in (depth, id) order after the sort (culled ones last)
     u32* idx_b;        // [P]
-    unsigned long long* counters;  // [4]: [0] = total tile instances, [1] = emit tile counter, [2..3] spare
-    u32* emit_status;  // [ceil(P/EMIT_TILE)] chained-scan words of the emit kernel
+    unsigned long long* counters;  // [4]: [0] = total tile instances, [1..3] spare
+    u32* emit_status;  // [ceil(P/EMIT_THREADS)] per-CTA tile-instance totals of the emit scan
     SortScratch sort;
     static size_t bytes(int P);
     static GeomState from(char* p, int P);
