@@ -34,6 +34,7 @@ constexpr u32 FULL = 0xffffffffu;
 // pixels per thread of the two blend kernels (1, 2 or 4); see bags_set_tuning
 static int g_fwd_ppt = 2;
 static int g_bwd_ppt = 2;
+static int g_cull = 1;   // 0: every splat of the tile list is evaluated for every patch (debugging / tests)
 
 // Tile decomposition.  Cell grid: 4 columns of 4 pixels x 8 rows of 2 pixels, bit = row * 4 + column.  Patch (x, y),
 // x in 0..1, y in 0..3, is the 8x4 pixel block at (8x, 4y) = cells {2x, 2x+1} x {2y, 2y+1} = bits 0x33 << (8y + 2x).
@@ -66,6 +67,20 @@ __device__ __forceinline__ u32 lds32(u32 a) {
     u32 v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
+}
+
+// power = -0.5 (a dx^2 + c dy^2) - b dx dy with exactly the operation order nvcc gives the reference's expression
+// (forward.cu:733, backward.cu:1041; checked against the reference cubin: c*dy*dy and b*dx*dy are rounded products,
+// a*dx*dx is fused into the sum, the final -0.5 scaling is fused with the cross term).  Threshold decisions
+// (alpha < 1/255, T < 1e-4) flip on the last bit, so the order is pinned with intrinsics instead of left to the
+// contraction choices of whatever surrounds the expression.  adx = a*dx and bdx = b*dx are shared by the pixels of a
+// thread (same column).
+__device__ __forceinline__ float splat_power(const float dx, const float adx, const float bdx, const float dy,
+                                             const float c) {
+    const float t = __fmul_rn(dy, __fmul_rn(dy, c));
+    const float s = __fmaf_rn(dx, adx, t);
+    const float u = __fmul_rn(dy, bdx);
+    return __fmaf_rn(s, -0.5f, -u);
 }
 
 // Cells of the tile at (tx0, ty0) that a splat can reach with alpha >= 1/255.
@@ -104,7 +119,8 @@ __device__ __forceinline__ u32 splat_cellmask(const float4 q0, const float4 con_
 template <int NT, bool WITH_ID>
 __device__ __forceinline__ void stage_batch(const u32* __restrict__ point_list, const float4* __restrict__ rec,
                                             const u32 first, const int dir, const int cnt, const float tx0,
-                                            const float ty0, float4* sm_rec, u32* sm_cell, u32* sm_id) {
+                                            const float ty0, float4* sm_rec, u32* sm_cell, u32* sm_id,
+                                            const bool cull) {
     for (int s = threadIdx.x; s < cnt; s += NT) {
         const u32 id = point_list[first + (u32)(dir * s)];
         const float4* r = rec + 3 * (size_t)id;
@@ -114,7 +130,7 @@ __device__ __forceinline__ void stage_batch(const u32* __restrict__ point_list, 
         sm_rec[3 * s + 0] = q0;
         sm_rec[3 * s + 1] = q1;
         sm_rec[3 * s + 2] = __ldg(r + 2);
-        sm_cell[s] = splat_cellmask(q0, q1, tx0, ty0);
+        sm_cell[s] = cull ? splat_cellmask(q0, q1, tx0, ty0) : 0xffffffffu;
     }
 }
 
@@ -123,7 +139,7 @@ __global__ void __launch_bounds__(256 / PPT)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float4* __restrict__ rec, float* __restrict__ final_T, u32* __restrict__ n_contrib,
                  const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_depth,
-                 float* __restrict__ out_alpha) {
+                 float* __restrict__ out_alpha, const bool cull) {
     constexpr int NT = 256 / PPT;
     __shared__ __align__(16) float4 sm_rec[BATCH * 3];
     __shared__ u32 sm_cell[BATCH];
@@ -164,7 +180,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
         if (num_done == NT) break;
 
         const int cnt = min(BATCH, toDo);
-        stage_batch<NT, false>(point_list, rec, range.x + (u32)(i * BATCH), 1, cnt, tx0, ty0, sm_rec, sm_cell, nullptr);
+        stage_batch<NT, false>(point_list, rec, range.x + (u32)(i * BATCH), 1, cnt, tx0, ty0, sm_rec, sm_cell, nullptr,
+                               cull);
         __syncthreads();
 
         // cells of the patches that still have unfinished pixels
@@ -189,12 +206,12 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                 const float4 q0 = lds128(a);
                 const float4 con_o = lds128(a + 16);
                 const float dx = q0.x - pxf;
+                const float adx = __fmul_rn(dx, con_o.x), bdx = __fmul_rn(dx, con_o.y);
 #pragma unroll
                 for (int k = 0; k < PPT; k++) {
                     if (((cm >> wp.cell_shift(k)) & 0x33u) == 0u) continue;  // warp-uniform
                     if (done[k]) continue;
-                    const float2 d = {dx, q0.y - pyf[k]};
-                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                    const float power = splat_power(dx, adx, bdx, q0.y - pyf[k], con_o.z);
                     if (power > 0.0f) continue;
                     const float alpha = min(0.99f, con_o.w * exp(power));
                     if (alpha < 1.0f / 255.0f) continue;
@@ -242,7 +259,8 @@ int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, Im
     dim3 grid(tiles_x(W), tiles_y(H), 1);
 #define BAGS_FWD(PPT)                                                                                            \
     blend_fwd_kernel<PPT><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, g.rec, img.final_T,        \
-                                                     img.n_contrib, bg, out_color, out_depth, out_alpha)
+                                                     img.n_contrib, bg, out_color, out_depth, out_alpha,       \
+                                                     g_cull != 0)
     if (g_fwd_ppt == 4) BAGS_FWD(4);
     else if (g_fwd_ppt == 2) BAGS_FWD(2);
     else BAGS_FWD(1);
@@ -297,7 +315,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                  const float* __restrict__ bg_color, const float4* __restrict__ rec,
                  const float* __restrict__ final_Ts, const u32* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
-                 const float* __restrict__ dL_dalphas, float* __restrict__ gacc) {
+                 const float* __restrict__ dL_dalphas, float* __restrict__ gacc, const bool cull) {
     constexpr int NT = 256 / PPT;
     constexpr int NW = NT / 32;
     __shared__ __align__(16) float4 sm_rec[BATCH * 3];
@@ -378,7 +396,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     for (int hi = (int)block_max; hi > 0; hi -= BATCH) {
         const int cnt = min(BATCH, hi);
         __syncthreads();  // everyone is done with the previous chunk
-        stage_batch<NT, true>(point_list, rec, range.x + (u32)(hi - 1), -1, cnt, tx0, ty0, sm_rec, sm_cell, sm_id);
+        stage_batch<NT, true>(point_list, rec, range.x + (u32)(hi - 1), -1, cnt, tx0, ty0, sm_rec, sm_cell, sm_id,
+                              cull);
         __syncthreads();
 
         // first slot this warp can contribute to: position hi-1-j < warp_max  <=>  j >= hi-warp_max
@@ -398,6 +417,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                 const float4 q0 = lds128(a);
                 const float4 con_o = lds128(a + 16);
                 const float dx = q0.x - pxf;
+                const float adx = __fmul_rn(dx, con_o.x), bdx = __fmul_rn(dx, con_o.y);
 
                 float v[16];
 #pragma unroll
@@ -408,7 +428,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                     // warp-uniform: does the splat's box reach this patch, and is the position still live there?
                     if (((cm >> wp.cell_shift(k)) & 0x33u) == 0u || pos >= pmax[k]) continue;
                     const float2 d = {dx, q0.y - (pyf0 + (float)(4 * k))};
-                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                    const float power = splat_power(dx, adx, bdx, d.y, con_o.z);
                     const float Gv = exp(power);
                     const float alpha = min(0.99f, con_o.w * Gv);
                     const bool valid = (pos < last_contributor[k]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
@@ -485,7 +505,8 @@ int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, co
     dim3 grid(tiles_x(W), tiles_y(H), 1);
 #define BAGS_BWD(PPT)                                                                                            \
     blend_bwd_kernel<PPT><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec, img.final_T,    \
-                                                     img.n_contrib, dL_dpix, dL_dpix_depth, dL_dalpha, gacc)
+                                                     img.n_contrib, dL_dpix, dL_dpix_depth, dL_dalpha, gacc,   \
+                                                     g_cull != 0)
     if (g_bwd_ppt == 4) BAGS_BWD(4);
     else if (g_bwd_ppt == 2) BAGS_BWD(2);
     else BAGS_BWD(1);
@@ -509,6 +530,11 @@ extern "C" int bags_debug_stats(unsigned long long* out, int reset) {
 #endif
 
 extern "C" int bags_set_tuning(int knob, int value) {
+    if (knob == BAGS_TUNE_BLEND_CULL) {
+        const int prev = bags::g_cull;
+        if (value == 0 || value == 1) bags::g_cull = value;
+        return prev;
+    }
     int* target = knob == BAGS_TUNE_BLEND_FWD_PPT ? &bags::g_fwd_ppt : knob == BAGS_TUNE_BLEND_BWD_PPT ? &bags::g_bwd_ppt : nullptr;
     if (!target) return BAGS_E_INVALID;
     const int prev = *target;

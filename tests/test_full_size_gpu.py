@@ -1,0 +1,178 @@
+"""Full-size parity on the B200 box: every BASELINE.json shape (C1..C5) against the live reference build, compared ON
+THE GPU so that the 10^7..10^8-element integer states do not have to travel to the host.
+
+Bars are the north-star's: radii / tiles_touched / sorted keys / point list / tile ranges / n_contrib bit-exact;
+image, depth, alpha max-abs <= 1e-5; gradients <= 1e-4 relative L2 (pose / intrinsic means: see test_parity_gpu.py).
+C5 (densification sweep 100k -> 6M at 1080p + distCUDA2 on 6M points) checks the integer state at every size and the
+k-NN distances bit for bit."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+import parity_common as pc
+
+S = pc.S
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not pc.ref_available(), reason="reference build (oracle/_ref) absent")]
+IMG_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _align(x, a=128):
+    return (x + a - 1) // a * a
+
+
+def ref_state_gpu(P, R, H, W, geom, binning, img):
+    """parity_common.parse_ref_state on device tensors (rasterizer_impl.cu:155-194 layout, 128-byte aligned fields)."""
+    N = H * W
+    out, off = {}, 0
+    off = _align(off + 4 * P)                                   # depths
+    off = _align(off + 3 * P)                                   # clamped
+    off = _align(off + 4 * P)                                   # internal_radii
+    off = _align(off + 8 * P)                                   # means2D
+    off = _align(off + 24 * P)                                  # cov3D
+    off = _align(off + 16 * P)                                  # conic_opacity
+    off = _align(off + 12 * P)                                  # rgb
+    out["tiles_touched"] = geom[off:off + 4 * P].view(torch.int32)
+    off = 0
+    out["final_T"] = img[off:off + 4 * N].view(torch.float32); off = _align(off + 4 * N)
+    out["n_contrib"] = img[off:off + 4 * N].view(torch.int32); off = _align(off + 4 * N)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    out["ranges"] = img[off:off + 8 * tiles].view(torch.int32).reshape(tiles, 2)
+    off = 0
+    out["point_list"] = binning[off:off + 4 * R].view(torch.int32); off = _align(off + 4 * R)
+    off = _align(off + 4 * R)                                   # point_list_unsorted
+    out["point_list_keys"] = binning[off:off + 8 * R].view(torch.int64)
+    return out
+
+
+def run_on_gpu(mod, cam, gs, up, dev, backward=True):
+    H, W = cam.H, cam.W
+    leaf = lambda t: t.to(dev).clone().requires_grad_(True)
+    L = dict(means3D=leaf(gs.means3D), opacities=leaf(gs.opacities), shs=leaf(gs.shs), scales=leaf(gs.scales),
+             rotations=leaf(gs.rotations), viewmatrix=leaf(cam.viewmatrix), projmatrix=leaf(cam.projmatrix),
+             campos=leaf(cam.campos), shift_factors=leaf(torch.tensor([1e-3, -5e-4, 2e-4])))
+    m2 = torch.zeros_like(L["means3D"], requires_grad=True)
+    m2d = torch.zeros_like(L["means3D"], requires_grad=True)
+    st = mod.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, torch.tensor([0.2, 0.4, 0.6], device=dev),
+                                           1.0, L["viewmatrix"], L["projmatrix"], cam.intrinsic.to(dev), 3,
+                                           L["campos"], False, False, 0)
+    color, radii, depth, weights, mean2D = mod.GaussianRasterizer(st)(
+        means3D=L["means3D"], means2D=m2, means2D_densify=m2d, shift_factors=L["shift_factors"],
+        opacities=L["opacities"], shs=L["shs"], scales=L["scales"], rotations=L["rotations"])
+    fn = color.grad_fn
+    R = fn.num_rendered
+    P = gs.means3D.shape[0]
+    geomB, binB, imgB = fn.saved_tensors[7], fn.saved_tensors[8], fn.saved_tensors[9]
+    if mod.__name__ == "ref_dgr":
+        state = ref_state_gpu(P, R, H, W, geomB, binB, imgB)
+    else:
+        state = mod._C.unpack_state(P, R, H, W, geomB, binB, imgB)
+    out = dict(color=color.detach(), radii=radii, depth=depth.detach(), weights=weights.detach(),
+               mean2D=mean2D.detach(), R=R, state={k: v.clone() for k, v in state.items()})
+    if backward:
+        dc, dd, da = [u.to(dev) for u in up]
+        torch.autograd.backward([color, depth, weights], [dc, dd, da])
+        out["grads"] = {k: v.grad.detach() for k, v in L.items() if v.grad is not None}
+        out["grads"]["means2D"] = m2.grad.detach()
+        out["grads"]["means2D_densify"] = m2d.grad.detach()
+    return out
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    n = b.norm()
+    return float((a - b).norm() / n) if float(n) > 0 else float((a - b).norm())
+
+
+def check_pair(o, r, grads=True):
+    assert o["R"] == r["R"]
+    assert torch.equal(o["radii"], r["radii"])
+    so, sr = o["state"], r["state"]
+    for k in ("tiles_touched", "point_list", "point_list_keys", "ranges", "n_contrib"):
+        assert torch.equal(so[k].reshape(-1), sr[k].reshape(-1)), k
+    assert float((so["final_T"] - sr["final_T"]).abs().max()) <= IMG_TOL
+    for k in ("color", "depth", "weights", "mean2D"):
+        assert float((o[k] - r[k]).abs().max()) <= IMG_TOL, k
+    if not grads:
+        return
+    for k, g in r["grads"].items():
+        if k == "viewmatrix":          # reference data race (Q13), covered by test_parity_gpu.py
+            continue
+        e = rel_l2(o["grads"][k], g)
+        if k in ("campos", "projmatrix", "shift_factors"):
+            # means over P of cancelling signed terms: the reference's fp32 .mean(0) is the limiting rounding
+            # (test_parity_gpu.py::_check_live); at 10^6 Gaussians allow 5e-6 * mean|term| ~ 1e-3 of the result
+            assert e <= 2e-3, (k, e)
+        else:
+            assert e <= GRAD_TOL, (k, e)
+
+
+FULL = [("C1", 0.004), ("C2", 0.004), ("C3", 0.004), ("C3", 0.012), ("C4", 0.004)]
+
+
+@pytest.mark.parametrize("name,scale", FULL, ids=[f"{n}-scale{s}" for n, s in FULL])
+def test_full_size_against_live_reference(name, scale):
+    c = S.CONFIGS[name]
+    dev = torch.device("cuda:0")
+    cam = S.make_camera(c["W"], c["H"])
+    gs = S.make_gaussians(c["P"], cam, scale=scale)
+    up = S.make_upstream(c["H"], c["W"])
+    o = run_on_gpu(pc.load_ours(), cam, gs, up, dev)
+    r = run_on_gpu(pc.load_ref(), cam, gs, up, dev)
+    check_pair(o, r)
+    del o, r
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("P", [100_000, 300_000, 1_000_000, 3_000_000, 6_000_000])
+def test_c5_densification_sweep(P):
+    """C5: the same 1080p camera while the scene grows 100k -> 6M Gaussians."""
+    dev = torch.device("cuda:0")
+    cam = S.make_camera(1920, 1080)
+    gs = S.make_gaussians(P, cam, scale=0.004)
+    up = S.make_upstream(1080, 1920)
+    o = run_on_gpu(pc.load_ours(), cam, gs, up, dev)
+    r = run_on_gpu(pc.load_ref(), cam, gs, up, dev)
+    check_pair(o, r)
+    del o, r
+    torch.cuda.empty_cache()
+
+
+def test_c5_knn_6m_points_bit_exact():
+    from simple_knn._C import distCUDA2
+    dd = os.path.join(pc.REF_DIR, "simple_knn")
+    spec = importlib.util.spec_from_file_location("ref_simple_knn._C", os.path.join(dd, "_C.so"))
+    refC = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refC)
+    g = torch.Generator().manual_seed(2)
+    pts = (torch.rand(6_000_000, 3, generator=g) * 10 - 5).to("cuda:0")
+    got = distCUDA2(pts)
+    want = refC.distCUDA2(pts)
+    assert torch.equal(got, want)
+
+
+def test_patch_culling_does_not_change_any_bit():
+    """The alpha >= 1/255 bounding-box culling of the blend kernels only skips pairs the reference skips too."""
+    import bags_capi
+    L = bags_capi.lib()
+    c = S.CONFIGS["C1"]
+    dev = torch.device("cuda:0")
+    cam = S.make_camera(c["W"], c["H"])
+    gs = S.make_gaussians(c["P"], cam, scale=0.006)
+    up = S.make_upstream(c["H"], c["W"])
+    res = {}
+    for cull in (1, 0):
+        prev = L.bags_set_tuning(2, cull)
+        try:
+            res[cull] = run_on_gpu(pc.load_ours(), cam, gs, up, dev)
+        finally:
+            L.bags_set_tuning(2, prev)
+    a, b = res[1], res[0]
+    for k in ("color", "depth", "weights"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(a["state"]["n_contrib"], b["state"]["n_contrib"])
+    assert torch.equal(a["state"]["final_T"], b["state"]["final_T"])
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        assert rel_l2(a["grads"][k], b["grads"][k]) <= 1e-5, k     # fp32 summation order only
