@@ -7,8 +7,8 @@ Contract (see DESIGN.md "Measurement"): a step = one training iteration over `vi
 (weak scaling): every view is rendered forward and back-propagated through the public GaussianRasterizer API, the
 Gaussian-parameter gradients accumulate in one flat buffer and (N>1) are summed with one NCCL all-reduce.
 `value` = views/s with the upstream image gradients resident in HBM; `e2e` = the same through host buffers: each
-view's ground-truth image comes from pinned host memory (H2D on a copy stream, prefetched one view ahead), the L1 loss
-is computed on the device and read back (D2H) inside the timed region.  Prints ONE JSON line on rank 0.
+view's 8-bit ground-truth image comes from pinned host memory (H2D on a copy stream, prefetched one view ahead), is
+converted to fp32 on the device, the L1 loss is computed on the device and read back (D2H) inside the timed region.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(S.CONFIGS))
     ap.add_argument("--views-per-gpu", type=int, default=4)
+    ap.add_argument("--P", type=int, default=0, help="override the Gaussian count of the config (C5 sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -181,7 +182,7 @@ def main():
         return 0
 
     cfg = S.CONFIGS[args.config]
-    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    P, W, H = args.P or cfg["P"], cfg["W"], cfg["H"]
     N = W * H
     vpg = args.views_per_gpu
     nviews = vpg * (world if args.impl == "ours" else 1)
@@ -199,12 +200,13 @@ def main():
     for v in my_views:
         cam = S.make_camera(W, H, seed=100 + v)
         g = torch.Generator().manual_seed(1000 + v)
-        gt_host = torch.rand(3, H, W, generator=g).pin_memory()
+        # ground truth as the dataset stores it: 8-bit RGB in pinned host memory, converted to fp32 on the device
+        gt_host = torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8).pin_memory()
         up = [u.to(dev) for u in S.make_upstream(H, W, seed=1 + v)]
         views.append(dict(
             view=cam.viewmatrix.to(dev).requires_grad_(True), proj=cam.projmatrix.to(dev).requires_grad_(True),
             campos=cam.campos.to(dev).requires_grad_(True), intrinsic=cam.intrinsic.to(dev), cam=cam,
-            gt_host=gt_host, gt_dev=torch.empty(3, H, W, device=dev), up=up))
+            gt_host=gt_host, gt_dev=torch.empty(3, H, W, device=dev, dtype=torch.uint8), up=up))
 
     def render(vw):
         st = mod.GaussianRasterizationSettings(
@@ -252,7 +254,7 @@ def main():
                 ev_next = issue_h2d(views[k + 1])
             color, radii, depth, weights, _ = render(vw)
             main.wait_event(ev)
-            loss = (color - vw["gt_dev"]).abs().mean()
+            loss = (color - vw["gt_dev"].float().mul_(1.0 / 255.0)).abs().mean()
             loss.backward()
             used = torch.cuda.Event()
             used.record(main)
@@ -317,7 +319,7 @@ def main():
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
         e2e = {"value": nviews * args.steps / (ms_e2e / 1e3), "unit": "views/s",
-               "h2d_bytes_per_step": len(views) * 3 * N * 4, "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": len(views) * 3 * N, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}
     clocks = sampler.stop() if sampler is not None else None
 

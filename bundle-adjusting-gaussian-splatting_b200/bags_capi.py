@@ -47,6 +47,15 @@ SIGNATURES = {
     "bags_compute_relocation": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "bags_knn_scratch_bytes": (c_size_t, [c_int]),
     "bags_knn_mean_dist2": (c_int, [c_int, _P, _P, _P, _P]),
+    "bags_distort_forward": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, _P, _P, _P, _P]),
+    "bags_distort_backward": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      _P, _P, _P, _P]),
+    "bags_center_crop_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "bags_center_crop_backward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "bags_loss_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bags_loss_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "bags_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_unpack_state": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bags_launch_count": (ctypes.c_ulonglong, []),

@@ -13,6 +13,11 @@
  *   bags_mark_visible             <- CudaRasterizer::Rasterizer::markVisible rasterizer.h:24-29, rasterize_points.cu:278-297
  *   bags_compute_relocation       <- UTILS::ComputeRelocation              3dgs-pose/cuda_rasterizer/utils.h, utils.cu:6-51
  *   bags_knn_mean_dist2           <- SimpleKNN::knn                        simple-knn/simple_knn.cu:185-221 (distCUDA2, spatial.cu:14-26)
+ *   bags_distort_forward/backward <- utils/util_distortion.py:271-311 (apply_distortion: F.interpolate of the control-
+ *                                    point flow + F.grid_sample of the render) and :58-77 (center_crop) -- the post-step
+ *                                    that --outside_rasterizer runs on every rendered canvas
+ *   bags_loss_forward/backward    <- utils/loss_utils.py:18-19 (l1_loss) and :49-76 (ssim / _ssim: five grouped 11x11
+ *                                    Gaussian convolutions + the SSIM map), combined at train.py:325
  *   bags_unpack_state             (test-only) exposes the private binning/image state so parity tests can compare
  *                                  tiles_touched / sorted keys / point list / ranges / n_contrib / final_T bit for bit
  *                                  with the reference's GeometryState/BinningState/ImageState (rasterizer_impl.h:21-72).
@@ -146,6 +151,41 @@ int bags_compute_relocation(int P, const float* opacity_old, const float* scale_
  * bags_knn_scratch_bytes(P) bytes. */
 size_t bags_knn_scratch_bytes(int P);
 int bags_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scratch, void* stream);
+
+/* Lens-distortion post-step (utils/util_distortion.py:271-311 + 58-77), fused:
+ *   flow(Hf,Wf,2) = bilinear upsample (align_corners=False) of `flow` [Hs,Ws,2]   (identity when Hs==Hf && Ws==Wf)
+ *   canvas        = grid_sample(image [C,H,W], flow, bilinear, zeros, align_corners=True)          -> [C,Hf,Wf]
+ *   out_image     = crop ? center_crop(canvas, Hc, Wc) (a second bilinear grid_sample) : canvas    -> [C,Hc,Wc]
+ *   out_mask[Hc,Wc] = mask_mode 0: !(out[0]==0 && out[1]==0)   mask_mode 1: !(out[0]<1e-5 && out[1]<1e-5)  (may be NULL)
+ *   out_flow [Hf,Wf,2] = the upsampled flow (may be NULL; apply_distortion returns it for reuse).
+ * 1 <= C <= 4.  With crop == 0, Hc/Wc must equal Hf/Wf.  Neither the canvas nor the upsampled flow is materialised.
+ * Backward: dL_dout [C,Hc,Wc] -> dL_dimage [C,H,W] and dL_dflow [Hs,Ws,2] (either may be NULL); both are zero-filled
+ * by the call and then accumulated with atomics like ATen's grid_sampler_2d_backward / upsample_bilinear2d_backward. */
+int bags_distort_forward(const float* image, int C, int H, int W, const float* flow, int Hs, int Ws, int Hf, int Wf,
+                         int Hc, int Wc, int crop, int mask_mode, float* out_image, float* out_mask, float* out_flow,
+                         void* stream);
+int bags_distort_backward(const float* image, int C, int H, int W, const float* flow, int Hs, int Ws, int Hf, int Wf,
+                          int Hc, int Wc, int crop, const float* dL_dout, float* dL_dimage, float* dL_dflow,
+                          void* stream);
+
+/* center_crop alone (utils/util_distortion.py:58-77), one image [C,H,W] -> [C,Hc,Wc]; backward writes every element
+ * of dL_dimage [C,H,W] (gather form, deterministic). */
+int bags_center_crop_forward(const float* image, int C, int H, int W, int Hc, int Wc, float* out, void* stream);
+int bags_center_crop_backward(const float* dL_dout, int C, int H, int W, int Hc, int Wc, float* dL_dimage,
+                              void* stream);
+
+/* Photometric loss (utils/loss_utils.py:18-19, 49-76), fused.  img1/img2: [planes][H][W] (planes = N*C).
+ * Forward: sums[plane] = {sum |img1-img2|, sum ssim_map} as doubles (fixed-order reduction; the caller divides by the
+ * element counts to get the reference's means).  want_ssim == 0 evaluates the L1 sum only.  d_mu1/d_e11/d_e12
+ * ([planes][H][W] each; all three or none) receive the partial derivatives of the SSIM map that the backward needs.
+ * `scratch` must hold bags_loss_scratch_bytes(planes, H, W) bytes.
+ * Backward: dL_dimg1 = coef[plane][0] * d(sum|.|)/dimg1 + coef[plane][1] * d(sum ssim_map)/dimg1, with coef a DEVICE
+ * array [planes][2] (the upstream gradients never visit the host).  Pass NULL maps for an L1-only backward. */
+size_t bags_loss_scratch_bytes(int planes, int H, int W);
+int bags_loss_forward(const float* img1, const float* img2, int planes, int H, int W, int want_ssim, float* d_mu1,
+                      float* d_e11, float* d_e12, char* scratch, double* sums, void* stream);
+int bags_loss_backward(const float* img1, const float* img2, int planes, int H, int W, const float* d_mu1,
+                       const float* d_e11, const float* d_e12, const float* coef, float* dL_dimg1, void* stream);
 
 /* Test-only view of the private state.  Any output pointer may be NULL.  All outputs are device pointers:
  *   tiles_touched [P] u32, depth_bits [P] u32 (float bits of the view-space depth, undefined for culled),

@@ -5,6 +5,7 @@
     python profiles/summarize_ncu.py full     gpurun_out/prof.ncu-rep   > profiles/rNN_<kernel>_ncu.txt
 """
 import csv
+import os
 import subprocess
 import sys
 from collections import Counter, OrderedDict
@@ -102,5 +103,55 @@ def full(path):
             i = j
 
 
+STAGE_OF = {"preprocess_fwd_kernel": "preprocess", "emit_count_kernel": "emit", "emit_scan_kernel": "emit",
+            "emit_fill_kernel": "emit", "tile_ranges_kernel": "ranges", "blend_fwd_kernel": "blend_fwd",
+            "blend_bwd_kernel": "blend_bwd", "preprocess_bwd_kernel": "preprocess_bwd",
+            "pose_finalize_kernel": "preprocess_bwd"}
+
+
+def traffic(path):
+    """Per-stage DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per view from an `ncu --set full` capture
+    of whole views (tools/ncu_target.py); the sort kernels are attributed to the depth sort until the emit kernels of
+    the view have run and to the tile sort afterwards.  Prints the JSON that bench.py reads (profiles/ncu_traffic.json)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+
+    def num(r, m):
+        v = float(r[ix[m]].replace(",", ""))
+        u = units[ix[m]]
+        return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "us": 1e-3, "ms": 1, "ns": 1e-6,
+                    "s": 1e3}.get(u, 1)
+
+    stages, views, sort_stage = OrderedDict(), 0, "depth_sort"
+    for r in rows[2:]:
+        name = r[ix["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
+        if name == "preprocess_fwd_kernel":
+            views += 1
+            sort_stage = "depth_sort"
+        if name in ("sort_hist_kernel", "onesweep_pass_kernel"):
+            st = sort_stage
+        elif name in STAGE_OF:
+            st = STAGE_OF[name]
+        else:
+            continue
+        if name == "emit_fill_kernel":
+            sort_stage = "tile_sort"
+        a = stages.setdefault(st, {"dram_bytes": 0.0, "ms": 0.0, "launches": 0})
+        a["dram_bytes"] += num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")
+        a["ms"] += num(r, "gpu__time_duration.sum")
+        a["launches"] += 1
+    views = max(views, 1)
+    out = {"_source": os.path.basename(path), "_views": views,
+           "_note": "per view: sums over the kernels of a stage divided by the number of captured views; ncu times are "
+                    "serialised and cold-cache"}
+    for st, a in stages.items():
+        out[st] = {"dram_bytes_per_launch": round(a["dram_bytes"] / views), "ncu_ms_per_view": round(a["ms"] / views, 4),
+                   "kernel_launches_per_view": a["launches"] / views}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])

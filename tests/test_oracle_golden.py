@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 from oracle import make_golden as MG  # noqa: E402
 from oracle import raster_oracle as O  # noqa: E402
 
-GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "tiny_*.npz")))
 
 
 def _scene(name):

@@ -23,7 +23,7 @@ from oracle import raster_oracle as O  # noqa: E402
 
 S = pc.S
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "tiny_*.npz")))
 IMG_TOL = 1e-5
 GRAD_TOL = 1e-4
 

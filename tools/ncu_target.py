@@ -15,7 +15,14 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.004
 c = S.CONFIGS["C3"]
 cam0 = S.make_camera(c["W"], c["H"], seed=100)
 gs = S.make_gaussians(c["P"], cam0, scale=scale)
-for v in range(n):
-    cam = S.make_camera(c["W"], c["H"], seed=100 + v)
-    o = pc.run_view(pc.load_ours(), cam, gs, S.make_upstream(c["H"], c["W"], seed=1 + v), torch.device("cuda:0"))
-    print("view", v, "R", o["num_rendered"])
+# one untimed pass first; with `ncu --profile-from-start off` only the second pass is captured
+for phase in ("warm", "profiled"):
+    if phase == "profiled":
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+    for v in range(n):
+        cam = S.make_camera(c["W"], c["H"], seed=100 + v)
+        o = pc.run_view(pc.load_ours(), cam, gs, S.make_upstream(c["H"], c["W"], seed=1 + v), torch.device("cuda:0"))
+        print(phase, "view", v, "R", o["num_rendered"])
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
