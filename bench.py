@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--P", type=int, default=0, help="override the Gaussian count of the config (C5 sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--trace", default="", help="development: write a GPU timeline summary of 2 device-leg and 2 "
+                                                "e2e steps (torch.profiler) to this JSON file; not a bench value")
     return ap.parse_args()
 
 
@@ -156,6 +158,47 @@ def cpu_baseline_sample():
     return {"value": n / dt, "unit": "views/s", "cores": os.cpu_count() or 1, "kind": "port",
             "sample": f"float64 PyTorch host oracle, {P} Gaussians SH3 at {W}x{H}, R={f['num_rendered']}, "
                       f"{n} fwd+bwd views in {dt:.1f}s (NOT the bench workload: a bounded sample)"}
+
+
+def trace_steps(fns, path):
+    """Development aid: GPU busy time, span and the kernels of 2 steps of each leg (CUPTI via torch.profiler)."""
+    from collections import defaultdict
+    from torch.profiler import ProfilerActivity, profile
+    out = {}
+    for name, fn in fns.items():
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            t0 = time.time()
+            for _ in range(2):
+                fn()
+            t_cpu = time.time() - t0
+            torch.cuda.synchronize()
+            t_wall = time.time() - t0
+        tmp = path + ".chrome.json"
+        prof.export_chrome_trace(tmp)
+        tr = json.load(open(tmp))
+        os.remove(tmp)
+        ev = [e for e in tr["traceEvents"] if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+        ev.sort(key=lambda e: e["ts"])
+        busy = sum(e["dur"] for e in ev)
+        span = (ev[-1]["ts"] + ev[-1]["dur"] - ev[0]["ts"]) if ev else 0
+        agg = defaultdict(lambda: [0, 0.0])
+        for e in ev:
+            a = agg[e["name"][:60]]
+            a[0] += 1
+            a[1] += e["dur"]
+        gaps = []
+        for a, b in zip(ev[:-1], ev[1:]):
+            g = b["ts"] - (a["ts"] + a["dur"])
+            if g > 20:
+                gaps.append({"after": a["name"][:40], "before": b["name"][:40], "us": round(g, 1)})
+        gaps.sort(key=lambda g: -g["us"])
+        out[name] = {"steps": 2, "gpu_busy_us": round(busy, 1), "gpu_span_us": round(span, 1),
+                     "cpu_issue_s": round(t_cpu, 5), "wall_s": round(t_wall, 5),
+                     "top": sorted(([k, v[0], round(v[1], 1)] for k, v in agg.items()), key=lambda r: -r[2])[:40],
+                     "gaps_over_20us": gaps[:40], "gap_total_us": round(sum(g["us"] for g in gaps), 1)}
+    json.dump(out, open(path, "w"), indent=1)
 
 
 def main():
@@ -334,6 +377,9 @@ def main():
         torch.cuda.synchronize()
         stage_ms, stage_calls = capi.profile_read()
         capi.lib().bags_profile_enable(0)
+
+    if args.trace and rank == 0:
+        trace_steps({"device": step_device, "e2e": step_e2e}, args.trace)
 
     if rank != 0:
         if use_dist:
