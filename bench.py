@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--P", type=int, default=0, help="override the Gaussian count of the config (C5 sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-grad-sinks", action="store_true",
+                    help="let autograd accumulate the Gaussian gradients (fresh tensors + adds) instead of the "
+                         "kernel adding into the flat gradient buffer")
     ap.add_argument("--trace", default="", help="development: write a GPU timeline summary of 2 device-leg and 2 "
                                                 "e2e steps (torch.profiler) to this JSON file; not a bench value")
     return ap.parse_args()
@@ -237,6 +240,9 @@ def main():
     import bags_view_parallel as VP
     params = VP.FlatGaussianParams(gs.means3D.to(dev), gs.shs.to(dev), gs.opacities.to(dev), gs.scales.to(dev),
                                    gs.rotations.to(dev), device=dev)
+    grad_sinks = args.impl == "ours" and not args.no_grad_sinks
+    if grad_sinks:
+        params.enable_direct_accumulation(mod)
     bg = torch.zeros(3, device=dev)
     shift = torch.zeros(3, device=dev, requires_grad=True)
     views = []
@@ -395,7 +401,9 @@ def main():
         "config": {"workload": f"{args.config}: {P} random Gaussians SH3, {W}x{H}, {vpg} views/GPU/step "
                                f"(fwd+bwd incl. pose/intrinsic grads), median scale {SCALE}",
                    "views_per_step": nviews, "visible_mean": V, "tile_instances_mean": R, "l2": "per-view working set (236 B x P inputs + state) "
-                   "exceeds the 126 MB L2; no explicit flush", "parallelism": f"view-dp{world}"},
+                   "exceeds the 126 MB L2; no explicit flush", "parallelism": f"view-dp{world}",
+                   "grad_accumulation": "kernel adds into the flat gradient buffer (register_grad_sink)" if grad_sinks
+                   else "autograd (fresh gradient tensors + add)"},
         "clocks": clocks,
     }
     if args.impl == "reference":

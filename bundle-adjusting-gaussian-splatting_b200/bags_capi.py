@@ -43,6 +43,11 @@ SIGNATURES = {
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,      # dense outputs
                                         _P, _P, _P, _P,                              # proj, view, campos, shift
                                         c_int, _P]),                                 # debug, stream
+    "bags_rasterize_backward_accum": (c_int, [c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P,
+                                              _P, c_float, _P, _P, _P, _P, _P, _P, c_float, c_float,
+                                              _P, _P, _P, _P, _P, _P, _P, _P,
+                                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                              ctypes.c_uint, c_int, _P]),   # + accumulate_mask before debug
     "bags_mark_visible": (c_int, [c_int, _P, _P, _P, _P, _P]),
     "bags_compute_relocation": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "bags_knn_scratch_bytes": (c_size_t, [c_int]),

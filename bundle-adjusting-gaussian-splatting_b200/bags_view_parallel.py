@@ -8,6 +8,7 @@ coupling is the sum of the Gaussian-parameter gradients.  This module provides e
 * ``FlatGaussianParams``  -- the Gaussian parameters as views into ONE contiguous fp32 buffer (59 floats per Gaussian:
   means3D 3 | SH 48 | opacity 1 | scales 3 | rotations 4) with ``.grad`` views into ONE contiguous gradient buffer, so
   autograd accumulates every view's gradients in place and a single all-reduce moves them (no pack step).
+  ``enable_direct_accumulation()`` additionally lets the backward kernel add into that buffer itself.
 * ``allreduce_gradients(params, group)``  -- one ``all_reduce(SUM)`` over that buffer (NCCL over NVLink on GPUs,
   gloo in the CPU tests).  Per-camera pose / intrinsic gradients are NOT reduced: each camera is owned by one rank.
 
@@ -57,6 +58,24 @@ class FlatGaussianParams:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+
+    def enable_direct_accumulation(self, rasterizer_module=None):
+        """Registers every parameter's gradient view as a gradient sink of the rasterizer
+        (diff_gaussian_rasterization.register_grad_sink): the backward kernel then adds each view's gradient straight
+        into the flat buffer -- bit-identical to autograd's `grad += new`, without the fresh tensors and the add
+        passes.  CUDA only (the sinks are a feature of the native library)."""
+        if rasterizer_module is None:
+            import diff_gaussian_rasterization as rasterizer_module
+        for name, _ in FIELDS:
+            rasterizer_module.register_grad_sink(self.params[name], self.params[name].grad)
+        self._sink_module = rasterizer_module
+
+    def disable_direct_accumulation(self):
+        m = getattr(self, "_sink_module", None)
+        if m is not None:
+            for name, _ in FIELDS:
+                m.unregister_grad_sink(self.params[name])
+            self._sink_module = None
 
 
 def allreduce_gradients(params: FlatGaussianParams, group=None, async_op: bool = False):

@@ -378,7 +378,7 @@ extern "C" int bags_rasterize_forward(
     return R;
 }
 
-extern "C" int bags_rasterize_backward(
+extern "C" int bags_rasterize_backward_accum(
     int P, int D, int M, int R, const float* background, int width, int height, const float* means3D,
     const float* shs, const float* colors_precomp, const float* alphas, const float* scales, float scale_modifier,
     const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
@@ -387,8 +387,10 @@ extern "C" int bags_rasterize_backward(
     const float* dL_dpix_depth, const float* dL_dalpha, char* scratch, float* dL_dmean2D, float* dL_dmean2D_densify,
     float* covariance, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
     float* dL_dscale, float* dL_drot, float* dL_dprojmatrix, float* dL_dviewmatrix, float* dL_dcampos,
-    float* dL_dshift, int debug, void* stream) {
+    float* dL_dshift, unsigned accumulate_mask, int debug, void* stream) {
     (void)intrinsic; (void)alphas; (void)colors_precomp;
+    BAGS_REQUIRE((accumulate_mask & ~(BAGS_ACC_MEANS3D | BAGS_ACC_SH | BAGS_ACC_OPACITY | BAGS_ACC_SCALE |
+                                      BAGS_ACC_ROT)) == 0, "unknown bit in accumulate_mask");
     cudaStream_t st = (cudaStream_t)stream;
     BAGS_REQUIRE(P >= 0 && R >= 0 && width > 0 && height > 0, "negative size");
     BAGS_REQUIRE(scratch && dL_dprojmatrix && dL_dviewmatrix && dL_dcampos && dL_dshift, "null pose output/scratch");
@@ -445,11 +447,29 @@ extern "C" int bags_rasterize_backward(
     int rc;
     {
         ProfScope ps(BAGS_STAGE_PREPROCESS_BWD, st);
-        rc = launch_preprocess_bwd(a, g, gacc, pose_acc, o, st);
+        rc = launch_preprocess_bwd(a, g, gacc, pose_acc, o, accumulate_mask, st);
     }
     if (rc) return rc;
     if (debug) BAGS_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
+}
+
+extern "C" int bags_rasterize_backward(
+    int P, int D, int M, int R, const float* background, int width, int height, const float* means3D,
+    const float* shs, const float* colors_precomp, const float* alphas, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+    const float* intrinsic, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer, const float* dL_dpix,
+    const float* dL_dpix_depth, const float* dL_dalpha, char* scratch, float* dL_dmean2D, float* dL_dmean2D_densify,
+    float* covariance, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+    float* dL_dscale, float* dL_drot, float* dL_dprojmatrix, float* dL_dviewmatrix, float* dL_dcampos,
+    float* dL_dshift, int debug, void* stream) {
+    return bags_rasterize_backward_accum(
+        P, D, M, R, background, width, height, means3D, shs, colors_precomp, alphas, scales, scale_modifier, rotations,
+        cov3D_precomp, viewmatrix, projmatrix, intrinsic, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+        binning_buffer, image_buffer, dL_dpix, dL_dpix_depth, dL_dalpha, scratch, dL_dmean2D, dL_dmean2D_densify,
+        covariance, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dprojmatrix,
+        dL_dviewmatrix, dL_dcampos, dL_dshift, 0u, debug, stream);
 }
 
 extern "C" int bags_unpack_state(int P, int R, int width, int height, const char* geom_buffer,

@@ -209,7 +209,7 @@ struct BwdOut {
 };
 // gacc: [P][16] accumulated by blend_bwd; pose_acc: [32] doubles (sums + winner), zeroed by the caller.
 int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, double* pose_acc,
-                          const BwdOut& o, cudaStream_t st);
+                          const BwdOut& o, unsigned accumulate_mask, cudaStream_t st);
 
 constexpr int GACC_STRIDE = 16;
 // gacc record layout (floats)

@@ -35,8 +35,11 @@ __host__ __device__ inline int sh_tile_stride(int M) { return (3 * M) | 1; }
 
 // Cooperative, coalesced copy between the per-warp SH tile (32 rows, one per Gaussian of the warp) and the
 // contiguous global block of the same 32 Gaussians.  `rows` = number of valid Gaussians (tail warp), `mask` selects
-// rows (loads only; stores are dense).  VEC = 4 needs 3M % 4 == 0 and a 16-byte aligned base.
-template <int VEC, bool LOAD>
+// rows (loads and accumulating stores; plain stores are dense).  VEC = 4 needs 3M % 4 == 0 and a 16-byte aligned
+// base.  SH_ACCUM adds the tile rows selected by `mask` onto what global memory holds (fp32 round-to-nearest adds,
+// the same operation as autograd's `grad += new`) and leaves the other rows untouched.
+enum { SH_LOAD = 0, SH_STORE = 1, SH_ACCUM = 2 };
+template <int VEC, int MODE>
 __device__ __forceinline__ void sh_tile_copy(float* tile, int stride, float* gptr, int row_len, int rows, u32 mask,
                                              int lane) {
     const int total = rows * row_len;
@@ -44,13 +47,23 @@ __device__ __forceinline__ void sh_tile_copy(float* tile, int stride, float* gpt
         const int row = f / row_len;
         const int col = f - row * row_len;
         float* t = tile + row * stride + col;
-        if (LOAD) {
+        if (MODE == SH_LOAD) {
             if (!((mask >> row) & 1u)) continue;
             if (VEC == 4) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(gptr + f));
                 t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
             } else {
                 t[0] = __ldg(gptr + f);
+            }
+        } else if (MODE == SH_ACCUM) {
+            if (!((mask >> row) & 1u)) continue;
+            if (VEC == 4) {
+                float4 v = *reinterpret_cast<const float4*>(gptr + f);
+                v.x = __fadd_rn(v.x, t[0]); v.y = __fadd_rn(v.y, t[1]);
+                v.z = __fadd_rn(v.z, t[2]); v.w = __fadd_rn(v.w, t[3]);
+                *reinterpret_cast<float4*>(gptr + f) = v;
+            } else {
+                gptr[f] = __fadd_rn(gptr[f], t[0]);
             }
         } else {
             if (VEC == 4) {
@@ -163,14 +176,19 @@ __device__ __forceinline__ void load_cov3d(int idx, const float* cov3D_precomp, 
     }
 }
 
-__global__ void __launch_bounds__(PB_THREADS)
+// ACCUM = false: `acc_mask` is ignored (every dense row is written).  ACCUM = true: the outputs selected by acc_mask
+// are accumulated (separate instantiation, so the plain path keeps its register count).
+template <bool ACCUM>
+__global__ void __launch_bounds__(PB_THREADS, 5)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
                       const float* __restrict__ shs, const float* __restrict__ scales,
                       const float* __restrict__ rotations, float scale_modifier,
                       const float* __restrict__ cov3D_precomp, const float* __restrict__ viewmatrix,
                       const float* __restrict__ projmatrix, const float* __restrict__ campos_ptr, int W, int H,
                       float tan_fovx, float tan_fovy, float focal_x, float focal_y, const float4* __restrict__ rec,
-                      const float* __restrict__ gacc, double* __restrict__ pose_acc, BwdOut o, int sh_vec4) {
+                      const float* __restrict__ gacc, double* __restrict__ pose_acc, BwdOut o, int sh_vec4,
+                      u32 acc_mask) {
+    const u32 acc = ACCUM ? acc_mask : 0u;
     extern __shared__ float sh_tiles[];           // [PB_WARPS][32][sh_tile_stride(M)]
     __shared__ float view[16];
     __shared__ float proj[16];
@@ -203,8 +221,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     const u32 vis_mask = __ballot_sync(0xffffffffu, lane_visible);
     if (shs != nullptr && rows > 0) {
         float* gsh = const_cast<float*>(shs) + (size_t)warp_first * sh_len;
-        if (sh_vec4) sh_tile_copy<4, true>(tile, stride, gsh, sh_len, rows, vis_mask, lane);
-        else sh_tile_copy<1, true>(tile, stride, gsh, sh_len, rows, vis_mask, lane);
+        if (sh_vec4) sh_tile_copy<4, SH_LOAD>(tile, stride, gsh, sh_len, rows, vis_mask, lane);
+        else sh_tile_copy<1, SH_LOAD>(tile, stride, gsh, sh_len, rows, vis_mask, lane);
         __syncwarp();
     }
 
@@ -444,13 +462,19 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
             pose[PA_SHIFT + 0] = dshift[0];
             pose[PA_SHIFT + 1] = dshift[1];
             pose[PA_SHIFT + 2] = dshift[2];
-        } else if (o.dL_dsh != nullptr && M > 0) {
+        } else if (o.dL_dsh != nullptr && M > 0 && !(acc & BAGS_ACC_SH)) {
             for (int k = 0; k < sh_len; k++) my_sh[k] = 0.f;
         }
 
-        // dense outputs, every row
+        // dense outputs, every row -- except the ones in accumulate mode (include/bags_b200.h, BAGS_ACC_*): those add
+        // the rows of visible Gaussians onto the caller's buffer and leave the rows of culled ones alone
+        if (!(acc & BAGS_ACC_MEANS3D)) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) o.dL_dmean3D[3 * i + k] = out_mean3D[k];
+            for (int k = 0; k < 3; k++) o.dL_dmean3D[3 * i + k] = out_mean3D[k];
+        } else if (visible) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) o.dL_dmean3D[3 * i + k] = __fadd_rn(o.dL_dmean3D[3 * i + k], out_mean3D[k]);
+        }
         o.dL_dmean2D[3 * i + 0] = out_mean2D[0];
         o.dL_dmean2D[3 * i + 1] = out_mean2D[1];
         o.dL_dmean2D[3 * i + 2] = 0.f;
@@ -459,22 +483,38 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         o.dL_dmean2D_densify[3 * i + 2] = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; k++) o.dL_dcolor[3 * i + k] = out_color[k];
-        o.dL_dopacity[i] = out_opacity;
+        if (!(acc & BAGS_ACC_OPACITY)) o.dL_dopacity[i] = out_opacity;
+        else if (visible) o.dL_dopacity[i] = __fadd_rn(o.dL_dopacity[i], out_opacity);
         o.covariance[i] = out_covariance;
 #pragma unroll
         for (int k = 0; k < 6; k++) o.dL_dcov3D[6 * i + k] = out_cov3D[k];
+        if (!(acc & BAGS_ACC_SCALE)) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) o.dL_dscale[3 * i + k] = out_scale[k];
+            for (int k = 0; k < 3; k++) o.dL_dscale[3 * i + k] = out_scale[k];
+        } else if (visible) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) o.dL_drot[4 * i + k] = out_rot[k];
+            for (int k = 0; k < 3; k++) o.dL_dscale[3 * i + k] = __fadd_rn(o.dL_dscale[3 * i + k], out_scale[k]);
+        }
+        if (!(acc & BAGS_ACC_ROT)) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) o.dL_drot[4 * i + k] = out_rot[k];
+        } else if (visible) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) o.dL_drot[4 * i + k] = __fadd_rn(o.dL_drot[4 * i + k], out_rot[k]);
+        }
     }
 
     // ---- dL_dSH: the warp's 32 rows leave as one contiguous, fully coalesced block ------------------------------
     if (o.dL_dsh != nullptr && M > 0 && rows > 0) {
         __syncwarp();
         float* gdst = o.dL_dsh + (size_t)warp_first * sh_len;
-        if (sh_vec4) sh_tile_copy<4, false>(tile, stride, gdst, sh_len, rows, 0xffffffffu, lane);
-        else sh_tile_copy<1, false>(tile, stride, gdst, sh_len, rows, 0xffffffffu, lane);
+        if (acc & BAGS_ACC_SH) {
+            if (sh_vec4) sh_tile_copy<4, SH_ACCUM>(tile, stride, gdst, sh_len, rows, vis_mask, lane);
+            else sh_tile_copy<1, SH_ACCUM>(tile, stride, gdst, sh_len, rows, vis_mask, lane);
+        } else {
+            if (sh_vec4) sh_tile_copy<4, SH_STORE>(tile, stride, gdst, sh_len, rows, 0xffffffffu, lane);
+            else sh_tile_copy<1, SH_STORE>(tile, stride, gdst, sh_len, rows, 0xffffffffu, lane);
+        }
     }
 
     // ---- pose terms: FP64 warp butterfly -> CTA -> one atomic per term -------------------------------------------
@@ -564,21 +604,21 @@ __global__ void pose_finalize_kernel(int P, const float* __restrict__ means3D, c
 }
 
 int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, double* pose_acc, const BwdOut& o,
-                          cudaStream_t st) {
+                          unsigned accumulate_mask, cudaStream_t st) {
     const int blocks = (a.P + PB_THREADS - 1) / PB_THREADS;
     const size_t smem = (size_t)PB_WARPS * 32 * sh_tile_stride(a.M) * sizeof(float);
     if (smem > 200 * 1024) {
         set_error("preprocess_bwd: %d SH coefficients per Gaussian do not fit the staging tile", a.M);
         return BAGS_E_INVALID;
     }
+    auto kern = accumulate_mask ? preprocess_bwd_kernel<true> : preprocess_bwd_kernel<false>;
     if (smem > 48 * 1024)
-        BAGS_CUDA_OK(cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
+        BAGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int vec4 = ((3 * a.M) % 4 == 0) && (((size_t)a.shs & 15) == 0) && (((size_t)o.dL_dsh & 15) == 0);
-    preprocess_bwd_kernel<<<blocks, PB_THREADS, smem, st>>>(
+    kern<<<blocks, PB_THREADS, smem, st>>>(
         a.P, a.D, a.M, a.means3D, a.radii, a.shs, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp,
         a.viewmatrix, a.projmatrix, a.campos, a.W, a.H, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, g.rec, gacc,
-        pose_acc, o, vec4);
+        pose_acc, o, vec4, (u32)accumulate_mask);
     BAGS_LAUNCH_OK("preprocess_bwd_kernel");
     pose_finalize_kernel<<<1, 32, 0, st>>>(a.P, a.means3D, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp,
                                            a.viewmatrix, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, gacc,

@@ -94,10 +94,21 @@ def rasterize_gaussians(background, means3D, shift_factors, colors, opacity, sca
     return (rendered, out_color, out_depth, out_alpha, radii, geom.t, binning.t, img.t, means2Dx, means2Dy)
 
 
+ACC_MEANS3D, ACC_SH, ACC_OPACITY, ACC_SCALE, ACC_ROT = 1, 2, 4, 8, 16     # BAGS_ACC_* of include/bags_b200.h
+
+
+def _sink_ok(buf, shape, dev):
+    return (buf is not None and buf.is_cuda and buf.device == dev and buf.dtype == torch.float32
+            and buf.is_contiguous() and tuple(buf.shape) == tuple(shape))
+
+
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, intrinsic, tan_fovx, tan_fovy, image_height,
                                  image_width, dL_dout_color, dL_dout_depth, dL_dout_alpha, sh, degree, campos,
-                                 geomBuffer, R, binningBuffer, imageBuffer, alphas, debug):
+                                 geomBuffer, R, binningBuffer, imageBuffer, alphas, debug, sinks=None):
+    """`sinks` (extension, default None = the reference's behaviour): dict name -> fp32 CUDA buffer for any of
+    means3D / sh / opacity / scales / rotations.  The gradient of a listed input is ADDED into its buffer by the
+    kernel (bags_rasterize_backward_accum) and None is returned in its slot of the tuple."""
     dev = means3D.device
     L = capi.lib()
     P = means3D.size(0)
@@ -121,22 +132,36 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
 
         M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
         f32 = dict(dtype=torch.float32, device=dev)
-        dL_dmeans3D = torch.empty((P, 3), **f32)
+        sinks = sinks or {}
+        acc = 0
+
+        def out(name, bit, shape):
+            nonlocal acc
+            buf = sinks.get(name)
+            if buf is None:
+                return torch.empty(shape, **f32), False
+            if not _sink_ok(buf, shape, dev):
+                raise RuntimeError(f"bags_b200: gradient sink for {name} must be a contiguous fp32 CUDA tensor of "
+                                   f"shape {tuple(shape)} on {dev}")
+            acc |= bit
+            return buf, True
+
+        dL_dmeans3D, s_means = out("means3D", ACC_MEANS3D, (P, 3))
         dL_dmeans2D = torch.empty((P, 3), **f32)
         dL_dmeans2D_densify = torch.empty((P, 3), **f32)
         dL_dcolors = torch.empty((P, NUM_CHANNELS), **f32)
         covariance = torch.empty((P, 1), **f32)
-        dL_dopacity = torch.empty((P, 1), **f32)
+        dL_dopacity, s_op = out("opacity", ACC_OPACITY, (P, 1))
         dL_dcov3D = torch.empty((P, 6), **f32)
-        dL_dsh = torch.empty((P, M, 3), **f32)
-        dL_dscales = torch.empty((P, 3), **f32)
-        dL_drotations = torch.empty((P, 4), **f32)
+        dL_dsh, s_sh = out("sh", ACC_SH, (P, M, 3))
+        dL_dscales, s_sc = out("scales", ACC_SCALE, (P, 3))
+        dL_drotations, s_rot = out("rotations", ACC_ROT, (P, 4))
         pose = torch.empty((38,), **f32)  # proj 16 | view 16 | campos 3 | shift 3
         scratch = torch.empty((int(L.bags_backward_scratch_bytes(P)),), dtype=torch.uint8, device=dev)
 
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         pp = pose.data_ptr()
-        rc = L.bags_rasterize_backward(
+        rc = L.bags_rasterize_backward_accum(
             P, int(degree), int(M), int(R),
             _ptr(background), W, H,
             _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(alphas),
@@ -149,10 +174,11 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             _ptr(dL_dmeans2D), _ptr(dL_dmeans2D_densify), _ptr(covariance), _ptr(dL_dopacity), _ptr(dL_dcolors),
             _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations),
             ctypes.c_void_p(pp), ctypes.c_void_p(pp + 64), ctypes.c_void_p(pp + 128), ctypes.c_void_p(pp + 140),
-            int(bool(debug)), stream)
-        capi.check(rc, "bags_rasterize_backward")
-    return (dL_dmeans2D, dL_dmeans2D_densify, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
-            dL_drotations, pose[32:35], pose[0:16], pose[16:32], pose[35:38], covariance)
+            acc, int(bool(debug)), stream)
+        capi.check(rc, "bags_rasterize_backward_accum")
+    return (dL_dmeans2D, dL_dmeans2D_densify, dL_dcolors, None if s_op else dL_dopacity,
+            None if s_means else dL_dmeans3D, dL_dcov3D, None if s_sh else dL_dsh, None if s_sc else dL_dscales,
+            None if s_rot else dL_drotations, pose[32:35], pose[0:16], pose[16:32], pose[35:38], covariance)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

@@ -44,18 +44,59 @@ class GaussianRasterizationSettings(NamedTuple):
     debug_iter: int
 
 
+# ---- gradient sinks (extension; off unless a caller registers one) ------------------------------------------------
+# The reference returns fresh gradient tensors and autograd then runs `param.grad += fresh` for each of the five
+# Gaussian parameters: three more passes over 236 B/Gaussian per view.  A caller that accumulates over views (gradient
+# accumulation, the view-parallel step of bags_view_parallel.py) can register the buffer a leaf's gradient is summed
+# into; the backward kernel then adds into that buffer directly and this input's autograd slot returns None.
+_GRAD_SINKS = {}        # (device index, data_ptr) -> (weakref to the leaf, buffer)
+
+
+def register_grad_sink(param, buffer):
+    """Accumulate the rasterizer's gradient w.r.t. `param` (a leaf passed as means3D / shs / opacities / scales /
+    rotations) directly into `buffer` (same shape, fp32, contiguous, same device).  Typically buffer is param.grad."""
+    import weakref
+    if not (param.is_cuda and buffer.is_cuda and param.device == buffer.device):
+        raise RuntimeError("bags_b200: gradient sinks need CUDA tensors on one device (there is no CPU path)")
+    if tuple(param.shape) != tuple(buffer.shape) or buffer.dtype != torch.float32 or not buffer.is_contiguous():
+        raise RuntimeError("bags_b200: a gradient sink must be a contiguous fp32 tensor of the parameter's shape")
+    _GRAD_SINKS[(param.device.index, param.data_ptr())] = (weakref.ref(param), buffer)
+
+
+def unregister_grad_sink(param):
+    _GRAD_SINKS.pop((param.device.index, param.data_ptr()), None)
+
+
+def _sink_of(t):
+    if not _GRAD_SINKS or t is None or not t.is_cuda or t.numel() == 0 or not t.requires_grad:
+        return None
+    ent = _GRAD_SINKS.get((t.device.index, t.data_ptr()))
+    if ent is None:
+        return None
+    ref, buf = ent
+    p = ref()
+    if p is None or p.data_ptr() != t.data_ptr() or tuple(p.shape) != tuple(t.shape) or not t.is_leaf:
+        return None
+    return buf
+
+
 def rasterize_gaussians(means3D, means2D, means2D_densify, shift_factors, sh, colors_precomp, opacities, scales,
                         rotations, cov3Ds_precomp, raster_settings):
+    sinks = None
+    if _GRAD_SINKS and torch.is_grad_enabled():
+        sinks = {k: b for k, b in (("means3D", _sink_of(means3D)), ("sh", _sink_of(sh)),
+                                   ("opacity", _sink_of(opacities)), ("scales", _sink_of(scales)),
+                                   ("rotations", _sink_of(rotations))) if b is not None} or None
     return _RasterizeGaussians.apply(
         means3D, means2D, means2D_densify, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
         raster_settings.viewmatrix, raster_settings.campos, raster_settings.projmatrix, shift_factors,
-        raster_settings)
+        raster_settings, sinks)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, means2D_densify, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, world_view, camera_center, full_proj, shift_factors, raster_settings):
+                cov3Ds_precomp, world_view, camera_center, full_proj, shift_factors, raster_settings, sinks=None):
         rs = raster_settings
         args = (rs.bg, means3D, shift_factors, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
                 cov3Ds_precomp, world_view, full_proj, rs.intrinsic, rs.tanfovx, rs.tanfovy, rs.image_height,
@@ -79,6 +120,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.camera_center = camera_center
         ctx.full_proj = full_proj
         ctx.world_view = world_view
+        ctx.grad_sinks = sinks
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
                               binningBuffer, imgBuffer, weights)
         return color, radii, depth, weights, mean2D
@@ -95,13 +137,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
-                out = _C.rasterize_gaussians_backward(*args)
+                out = _C.rasterize_gaussians_backward(*args, sinks=ctx.grad_sinks)
             except Exception:
                 torch.save(cpu_args, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise
         else:
-            out = _C.rasterize_gaussians_backward(*args)
+            out = _C.rasterize_gaussians_backward(*args, sinks=ctx.grad_sinks)
         (grad_means2D, grad_means2D_densify, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp,
          grad_sh, grad_scales, grad_rotations, grad_camera_center, grad_full_proj, grad_world_view,
          grad_shift_factors, covariance) = out
@@ -111,7 +153,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         return (grad_means3D, grad_means2D, grad_means2D_densify, grad_sh, grad_colors_precomp, grad_opacities,
                 grad_scales, grad_rotations, grad_cov3Ds_precomp, grad_world_view, grad_camera_center,
-                grad_full_proj, grad_shift_factors, None)
+                grad_full_proj, grad_shift_factors, None, None)
 
 
 class GaussianRasterizer(nn.Module):

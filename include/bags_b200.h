@@ -139,6 +139,59 @@ int bags_rasterize_backward(
     int debug,
     void* stream);
 
+/* Gradient accumulation (extension; the reference returns fresh tensors and leaves `.grad += new` to autograd, three
+ * extra passes over 236 B/Gaussian per view).  Same contract as bags_rasterize_backward, except that every output
+ * selected in `accumulate_mask` (BAGS_ACC_*) is ADDED to what the caller's buffer already holds: rows of visible
+ * Gaussians are updated with one fp32 round-to-nearest add per element (bit-identical to `buffer += fresh gradient`),
+ * rows of culled Gaussians are neither read nor written.  accumulate_mask == 0 is bags_rasterize_backward. */
+#define BAGS_ACC_MEANS3D 1u
+#define BAGS_ACC_SH 2u
+#define BAGS_ACC_OPACITY 4u
+#define BAGS_ACC_SCALE 8u
+#define BAGS_ACC_ROT 16u
+int bags_rasterize_backward_accum(
+    int P, int D, int M, int R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* alphas,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* intrinsic,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    const char* geom_buffer,
+    const char* binning_buffer,
+    const char* image_buffer,
+    const float* dL_dpix,
+    const float* dL_dpix_depth,
+    const float* dL_dalpha,
+    char* scratch,
+    float* dL_dmean2D,
+    float* dL_dmean2D_densify,
+    float* covariance,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    float* dL_dprojmatrix,
+    float* dL_dviewmatrix,
+    float* dL_dcampos,
+    float* dL_dshift,
+    unsigned accumulate_mask,
+    int debug,
+    void* stream);
+
 /* present[i] = (view * p_i).z > 0.2  (auxiliary.h:139-164).  `present` is one byte per point. */
 int bags_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                       uint8_t* present, void* stream);

@@ -390,3 +390,83 @@ def test_knn_dist2_matches_bruteforce_and_reference():
         c = torch.randn(50000, 3, generator=g) * 0.01 + torch.randint(0, 5, (50000, 1), generator=g).float()
         c = c.to(d)
         assert torch.equal(distCUDA2(c), refC.distCUDA2(c))
+
+
+@pytest.mark.parametrize("sh_degree", [3, 1])
+def test_gradient_sinks_equal_autograd_accumulation(sh_degree):
+    """register_grad_sink / bags_rasterize_backward_accum: three views accumulated by the kernel into a flat gradient
+    buffer == the same three views accumulated by autograd (`grad += fresh`), BIT for bit (one fp32 add per element in
+    the same order); culled rows are untouched; pose gradients and the non-sunk outputs are unchanged."""
+    import bags_view_parallel as VP
+    mod = pc.load_ours()
+    d = dev()
+    W, H, P = 320, 208, 20000
+    cam0 = S.make_camera(W, H, seed=100)
+    gs = S.make_gaussians(P, cam0, seed=0, scale=0.02)
+    cams = [S.make_camera(W, H, seed=100 + v) for v in range(3)]
+    ups = [[u.to(d) for u in S.make_upstream(H, W, seed=1 + v)] for v in range(3)]
+
+    def run(direct):
+        params = VP.FlatGaussianParams(gs.means3D.to(d), gs.shs.to(d), gs.opacities.to(d), gs.scales.to(d),
+                                       gs.rotations.to(d), device=d)
+        if direct:
+            params.enable_direct_accumulation(mod)
+        params.flat_grad.fill_(0.25)            # a non-zero start value: accumulation must ADD, not overwrite
+        pose, m2d_grads, radii_all = [], [], []
+        shift = torch.zeros(3, device=d, requires_grad=True)
+        try:
+            for cam, up in zip(cams, ups):
+                view = cam.viewmatrix.to(d).requires_grad_(True)
+                proj = cam.projmatrix.to(d).requires_grad_(True)
+                campos = cam.campos.to(d).requires_grad_(True)
+                st = mod.GaussianRasterizationSettings(
+                    image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                    bg=torch.zeros(3, device=d), scale_modifier=1.0, viewmatrix=view, projmatrix=proj,
+                    intrinsic=cam.intrinsic.to(d), sh_degree=sh_degree, campos=campos, prefiltered=False, debug=False,
+                    debug_iter=0)
+                m2d = torch.zeros_like(params["means3D"], requires_grad=True)
+                m2dd = torch.zeros_like(params["means3D"], requires_grad=True)
+                color, radii, depth, weights, _ = mod.GaussianRasterizer(raster_settings=st)(
+                    means3D=params["means3D"], means2D=m2d, means2D_densify=m2dd, shift_factors=shift,
+                    opacities=params["opacities"], shs=params["shs"], scales=params["scales"],
+                    rotations=params["rotations"])
+                torch.autograd.backward([color, depth, weights], up)
+                pose.append(torch.cat([view.grad.flatten(), proj.grad.flatten(), campos.grad]).cpu())
+                m2d_grads.append(torch.cat([m2d.grad, m2dd.grad], 1).cpu())
+                radii_all.append(radii.cpu())
+        finally:
+            params.disable_direct_accumulation()
+        return params.flat_grad.cpu(), pose, m2d_grads, shift.grad.cpu(), radii_all, params
+
+    import bags_capi
+    n0 = bags_capi.lib().bags_launch_count()
+    g_direct, pose_d, m2d_d, shift_d, radii, params = run(True)
+    assert bags_capi.lib().bags_launch_count() > n0
+    g_auto, pose_a, m2d_a, shift_a, _, _ = run(False)
+    assert torch.equal(g_direct.view(torch.int32), g_auto.view(torch.int32)) or torch.equal(g_direct, g_auto)
+    assert float((g_direct - g_auto).abs().max()) == 0.0
+    for a, b in zip(pose_d, pose_a):
+        assert torch.equal(a, b)
+    for a, b in zip(m2d_d, m2d_a):
+        assert torch.equal(a, b)
+    assert torch.equal(shift_d, shift_a)
+    # rows culled in every view still hold the start value; visible rows moved
+    never = torch.stack([r <= 0 for r in radii]).all(0)
+    assert int(never.sum()) > 0 and int((~never).sum()) > 0
+    gm = g_direct[:3 * P].view(P, 3)
+    assert bool((gm[never] == 0.25).all())
+    assert float((gm[~never] - 0.25).abs().max()) > 0
+    # the leaves' .grad ARE the flat buffer (autograd did not replace them)
+    assert params["means3D"].grad.data_ptr() == params.flat_grad.data_ptr()
+
+
+def test_gradient_sink_rejects_bad_buffers():
+    mod = pc.load_ours()
+    d = dev()
+    p = torch.zeros(10, 3, device=d, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        mod.register_grad_sink(p, torch.zeros(10, 4, device=d))
+    with pytest.raises(RuntimeError):
+        mod.register_grad_sink(p, torch.zeros(10, 3, device=d, dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        mod.register_grad_sink(p.detach().cpu().requires_grad_(True), torch.zeros(10, 3))
