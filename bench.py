@@ -8,7 +8,9 @@ Contract (see DESIGN.md "Measurement"): a step = one training iteration over `vi
 Gaussian-parameter gradients accumulate in one flat buffer and (N>1) are summed with one NCCL all-reduce.
 `value` = views/s with the upstream image gradients resident in HBM; `e2e` = the same through host buffers: each
 view's 8-bit ground-truth image comes from pinned host memory (H2D on a copy stream, prefetched one view ahead), is
-converted to fp32 on the device, the L1 loss is computed on the device and read back (D2H) inside the timed region.  Prints ONE JSON line on rank 0.
+converted to fp32 on the device, the L1 loss (ours: bags_loss.l1_loss, the drop-in for utils/loss_utils.py; reference
+arm: the torch operator sequence of utils/loss_utils.py:18-19) is computed on the device and read back (D2H) inside
+the timed region.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -45,6 +47,8 @@ def parse():
     ap.add_argument("--no-grad-sinks", action="store_true",
                     help="let autograd accumulate the Gaussian gradients (fresh tensors + adds) instead of the "
                          "kernel adding into the flat gradient buffer")
+    ap.add_argument("--torch-loss", action="store_true",
+                    help="e2e leg: L1 loss as torch operators (what the reference arm runs) instead of bags_loss")
     ap.add_argument("--trace", default="", help="development: write a GPU timeline summary of 2 device-leg and 2 "
                                                 "e2e steps (torch.profiler) to this JSON file; not a bench value")
     return ap.parse_args()
@@ -279,6 +283,12 @@ def main():
             VP.allreduce_gradients(params)
 
     copy_stream = torch.cuda.Stream(device=dev)
+    if args.impl == "ours" and not args.torch_loss:
+        import bags_loss          # drop-in for utils/loss_utils.py:l1_loss (fused forward/backward kernels)
+        l1_loss = bags_loss.l1_loss
+    else:
+        def l1_loss(network_output, gt):   # utils/loss_utils.py:18-19, the operator sequence the reference runs
+            return torch.abs(network_output - gt).mean()
 
     def issue_h2d(vw):
         """host->device copy of one view's ground truth on the copy stream (after the previous reader of the buffer)"""
@@ -303,7 +313,7 @@ def main():
                 ev_next = issue_h2d(views[k + 1])
             color, radii, depth, weights, _ = render(vw)
             main.wait_event(ev)
-            loss = (color - vw["gt_dev"].float().mul_(1.0 / 255.0)).abs().mean()
+            loss = l1_loss(color, vw["gt_dev"].float().mul_(1.0 / 255.0))
             loss.backward()
             used = torch.cuda.Event()
             used.record(main)

@@ -26,7 +26,8 @@ namespace bags {
 // look-back with several predecessors in flight per round.
 // =================================================================================================================
 constexpr size_t SORT_SMEM_BYTES = (2 * SORT_TILE + SORT_WARPS * RADIX + 2 * RADIX + 8) * sizeof(u32);
-constexpr int SORT_LOOKBACK = 8;     // predecessor status words fetched per look-back round (memory-level parallelism)
+constexpr int SORT_LOOKBACK_FIRST = 8;   // predecessor status words fetched in the first look-back round
+static int g_sort_lookback = 32;         // ... and in every later round (8, 16, 32 or 64; see bags_set_tuning)
 constexpr u32 FLAG_AGG = 1u << 30;   // tile aggregate available
 constexpr u32 FLAG_INCL = 2u << 30;  // inclusive prefix available
 constexpr u32 VAL_MASK = (1u << 30) - 1;
@@ -98,7 +99,31 @@ __device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32* warp_tot /*[8] sm
     return base + inc - v;
 }
 
-template <bool IOTA>
+// One look-back round for digit `tid`: K predecessor status words are loaded at once (independent loads), then
+// consumed nearest first; a word that is not published yet is polled.  Returns true once an inclusive prefix (or
+// the start of the array) has been reached.
+template <int K>
+__device__ __forceinline__ bool lookback_round(const u32* __restrict__ status, const int tid, int& look, u32& excl) {
+    u32 sw[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int t = look - k;
+        sw[k] = (t >= 0) ? ld_volatile_u32(status + (size_t)t * RADIX + tid) : FLAG_INCL;
+    }
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (done) continue;
+        u32 v = sw[k];
+        while ((v & ~VAL_MASK) == 0) v = ld_volatile_u32(status + (size_t)(look - k) * RADIX + tid);
+        excl += v & VAL_MASK;
+        if ((v & ~VAL_MASK) == FLAG_INCL) done = true;
+    }
+    look -= K;
+    return done;
+}
+
+template <bool IOTA, int LOOKBACK>
 __global__ void __launch_bounds__(SORT_THREADS, 4)
 onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, u32* __restrict__ keys_out,
                      u32* __restrict__ vals_out, int n, int shift, int bits, const u32* __restrict__ ghist,
@@ -176,27 +201,15 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
         u32 excl = 0;
         if (tile > 0) {
             st_volatile_u32(st, sum | FLAG_AGG);
-            // Decoupled look-back, SORT_LOOKBACK predecessors per round: the loads of a round are independent, so a
-            // walk over k tiles costs about k / SORT_LOOKBACK memory round trips instead of k.
+            // Decoupled look-back, several predecessors per round: the loads of a round are independent, so a walk
+            // over k tiles costs about k / LOOKBACK memory round trips instead of k.  When a whole wave of CTAs
+            // publishes its aggregates at the same time, the front of inclusive prefixes advances LOOKBACK tiles per
+            // round trip and tile k resolves after about k / (2 LOOKBACK) of them: with 8 words per round that chain
+            // (~600 resident tiles) was most of a pass's duration.  The first round stays short for the common late
+            // case (the nearest predecessors already hold inclusive prefixes).
             int look = (int)tile - 1;
-            bool done = false;
-            while (!done) {
-                u32 sw[SORT_LOOKBACK];
-#pragma unroll
-                for (int k = 0; k < SORT_LOOKBACK; k++) {
-                    const int t = look - k;
-                    sw[k] = (t >= 0) ? ld_volatile_u32(status + (size_t)t * RADIX + tid) : FLAG_INCL;
-                }
-#pragma unroll
-                for (int k = 0; k < SORT_LOOKBACK; k++) {
-                    if (done) continue;
-                    u32 v = sw[k];
-                    while ((v & ~VAL_MASK) == 0) v = ld_volatile_u32(status + (size_t)(look - k) * RADIX + tid);
-                    excl += v & VAL_MASK;
-                    if ((v & ~VAL_MASK) == FLAG_INCL) done = true;
-                }
-                look -= SORT_LOOKBACK;
-            }
+            bool done = lookback_round<SORT_LOOKBACK_FIRST>(status, tid, look, excl);
+            while (!done) done = lookback_round<LOOKBACK>(status, tid, look, excl);
         }
         st_volatile_u32(st, ((excl + sum) & VAL_MASK) | FLAG_INCL);
 
@@ -253,23 +266,32 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
     BAGS_LAUNCH_OK("sort_hist_kernel");
     const int ntiles = (n + SORT_TILE - 1) / SORT_TILE;
     // per-device attribute; setting it is a cheap driver call, so do it on every sort (multi-device safe)
-    BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)SORT_SMEM_BYTES));
-    BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)SORT_SMEM_BYTES));
     u32 *ki = keys_in, *vi = vals_in, *ko = keys_out, *vo = vals_out;
     for (int p = 0; p < npass; p++) {
         int sft = begin_bit + p * RADIX_BITS;
         int bits = min(RADIX_BITS, end_bit - sft);
         u32* status = sc.status + (size_t)p * sc.ntiles * RADIX;
-        if (p == 0 && iota_vals)
-            onesweep_pass_kernel<true><<<ntiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(ki, vi, ko, vo, n, sft, bits,
-                                                                        sc.ghist + p * RADIX, sc.tile_counter + p,
-                                                                        status);
-        else
-            onesweep_pass_kernel<false><<<ntiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(ki, vi, ko, vo, n, sft, bits,
-                                                                         sc.ghist + p * RADIX, sc.tile_counter + p,
-                                                                         status);
+        const bool iota = p == 0 && iota_vals;
+        // the shared-memory attribute is per device; setting it is a cheap driver call, so do it on every launch
+        // (multi-device safe)
+#define BAGS_PASS(IOTA, LB)                                                                                        \
+    do {                                                                                                           \
+        BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB>,                                          \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_BYTES));     \
+        onesweep_pass_kernel<IOTA, LB><<<ntiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(                             \
+            ki, vi, ko, vo, n, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status);                      \
+    } while (0)
+#define BAGS_PASS_LB(LB)                                                                                           \
+    do {                                                                                                           \
+        if (iota) BAGS_PASS(true, LB);                                                                             \
+        else BAGS_PASS(false, LB);                                                                                 \
+    } while (0)
+        if (g_sort_lookback == 8) BAGS_PASS_LB(8);
+        else if (g_sort_lookback == 16) BAGS_PASS_LB(16);
+        else if (g_sort_lookback == 64) BAGS_PASS_LB(64);
+        else BAGS_PASS_LB(32);
+#undef BAGS_PASS_LB
+#undef BAGS_PASS
         BAGS_LAUNCH_OK("onesweep_pass_kernel");
         u32* t;
         t = ki; ki = ko; ko = t;
@@ -488,6 +510,12 @@ int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cuda
         BAGS_LAUNCH_OK("tile_ranges_kernel");
     }
     return 0;
+}
+
+int set_sort_lookback(int value) {
+    const int prev = g_sort_lookback;
+    if (value == 8 || value == 16 || value == 32 || value == 64) g_sort_lookback = value;
+    return prev;
 }
 
 }  // namespace bags

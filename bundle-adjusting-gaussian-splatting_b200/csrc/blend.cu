@@ -535,6 +535,7 @@ extern "C" int bags_set_tuning(int knob, int value) {
         if (value == 0 || value == 1) bags::g_cull = value;
         return prev;
     }
+    if (knob == BAGS_TUNE_SORT_LOOKBACK) return bags::set_sort_lookback(value);
     int* target = knob == BAGS_TUNE_BLEND_FWD_PPT ? &bags::g_fwd_ppt : knob == BAGS_TUNE_BLEND_BWD_PPT ? &bags::g_bwd_ppt : nullptr;
     if (!target) return BAGS_E_INVALID;
     const int prev = *target;

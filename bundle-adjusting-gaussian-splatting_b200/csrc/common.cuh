@@ -169,6 +169,7 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
 int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st);
 int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, const u32* offsets, BinningState& b,
                      int grid_x, cudaStream_t st);
+int set_sort_lookback(int value);
 int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st);
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);

@@ -276,9 +276,11 @@ int bags_profile_read(double* ms, unsigned long long* calls);
  * (1, 2 or 4; a warp owns that many 8x4 patches of the tile).  Results do not depend on them beyond the fp32
  * summation order of the gradients.  BLEND_CULL: 1 (default) skips, per 8x4 patch, the splats whose alpha >= 1/255
  * bounding box misses the patch; 0 evaluates every splat of the tile list for every patch (must give the same forward
- * bits -- used by the tests).  Returns the previous value (other values only query), BAGS_E_INVALID for an
- * unknown knob. */
-enum { BAGS_TUNE_BLEND_FWD_PPT = 0, BAGS_TUNE_BLEND_BWD_PPT = 1, BAGS_TUNE_BLEND_CULL = 2 };
+ * bits -- used by the tests).  SORT_LOOKBACK: predecessor status words the onesweep passes fetch per look-back
+ * round (8, 16, 32 or 64; default 32; no effect on results).  Returns the previous value (other values only
+ * query), BAGS_E_INVALID for an unknown knob. */
+enum { BAGS_TUNE_BLEND_FWD_PPT = 0, BAGS_TUNE_BLEND_BWD_PPT = 1, BAGS_TUNE_BLEND_CULL = 2,
+       BAGS_TUNE_SORT_LOOKBACK = 3 };
 int bags_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -33,7 +33,7 @@ def center_crop(tensor, target_height, target_width):
                                     torch.linspace(start_x, start_x + target_width - 1, target_width), indexing="ij")
     grid = torch.stack((grid_x, grid_y), 2).unsqueeze(0)
     grid = 2.0 * grid / torch.tensor([width - 1, height - 1]) - 1.0
-    grid = grid.expand(tensor.size(0), target_height, target_width, 2).to(tensor.dtype)
+    grid = grid.expand(tensor.size(0), target_height, target_width, 2).to(device=tensor.device, dtype=tensor.dtype)
     return F.grid_sample(tensor, grid, align_corners=True)
 
 
@@ -81,7 +81,7 @@ def _window(window_size, channel, dtype):
 def ssim(img1, img2, window_size=11, size_average=True):
     """utils/loss_utils.py:49-76 for (C,H,W) or (N,C,H,W) inputs."""
     channel = img1.size(-3)
-    window = _window(window_size, channel, img1.dtype)
+    window = _window(window_size, channel, img1.dtype).to(img1.device)
     squeeze = img1.dim() == 3
     if squeeze:
         img1, img2 = img1.unsqueeze(0), img2.unsqueeze(0)

@@ -395,8 +395,8 @@ def test_knn_dist2_matches_bruteforce_and_reference():
 @pytest.mark.parametrize("sh_degree", [3, 1])
 def test_gradient_sinks_equal_autograd_accumulation(sh_degree):
     """register_grad_sink / bags_rasterize_backward_accum: three views accumulated by the kernel into a flat gradient
-    buffer == the same three views accumulated by autograd (`grad += fresh`), BIT for bit (one fp32 add per element in
-    the same order); culled rows are untouched; pose gradients and the non-sunk outputs are unchanged."""
+    buffer == the same three views accumulated by autograd (`grad += fresh`) up to the run-to-run atomic-order noise
+    of the per-view gradients; culled rows are untouched (exactly); pose gradients and the non-sunk outputs agree."""
     import bags_view_parallel as VP
     mod = pc.load_ours()
     d = dev()
@@ -443,13 +443,15 @@ def test_gradient_sinks_equal_autograd_accumulation(sh_degree):
     g_direct, pose_d, m2d_d, shift_d, radii, params = run(True)
     assert bags_capi.lib().bags_launch_count() > n0
     g_auto, pose_a, m2d_a, shift_a, _, _ = run(False)
-    assert torch.equal(g_direct.view(torch.int32), g_auto.view(torch.int32)) or torch.equal(g_direct, g_auto)
-    assert float((g_direct - g_auto).abs().max()) == 0.0
+    # The accumulation itself is one fp32 add per element in the same order as autograd's `grad += fresh`, but the
+    # per-view gradients are sums of red.global.add commits whose order changes from run to run (like the
+    # reference's atomicAdds), so two runs agree to fp32 summation noise, not bit for bit.
+    assert pc.rel_l2(g_direct - 0.25, g_auto - 0.25) <= 1e-5
     for a, b in zip(pose_d, pose_a):
-        assert torch.equal(a, b)
+        assert pc.rel_l2(a, b) <= 1e-5
     for a, b in zip(m2d_d, m2d_a):
-        assert torch.equal(a, b)
-    assert torch.equal(shift_d, shift_a)
+        assert pc.rel_l2(a, b) <= 1e-5
+    assert pc.rel_l2(shift_d, shift_a) <= 1e-5 or float((shift_d - shift_a).abs().max()) == 0.0
     # rows culled in every view still hold the start value; visible rows moved
     never = torch.stack([r <= 0 for r in radii]).all(0)
     assert int(never.sum()) > 0 and int((~never).sum()) > 0

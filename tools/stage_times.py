@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--views", type=int, default=6)
     ap.add_argument("--ppt", default="1:1,2:2,2:4,4:4,1:4", help="fwd:bwd pixels per thread")
     ap.add_argument("--P", type=int, default=0)
+    ap.add_argument("--tune", default="", help="extra knob settings tried in turn, e.g. 3=8,3=32 (knob=value)")
     a = ap.parse_args()
     cfg = S.CONFIGS[a.config]
     P, W, H = a.P or cfg["P"], cfg["W"], cfg["H"]
@@ -55,7 +56,10 @@ def main():
         return R, int((radii > 0).sum())
 
     L = capi.lib()
-    for G in a.ppt.split(","):
+    groups = [(G, t) for t in (a.tune.split(",") if a.tune else [""]) for G in a.ppt.split(",")]
+    for G, tune in groups:
+        if tune:
+            L.bags_set_tuning(int(tune.split("=")[0]), int(tune.split("=")[1]))
         L.bags_set_tuning(0, int(G.split(":")[0]))
         L.bags_set_tuning(1, int(G.split(":")[1]))
         for vw in views[:2]:
@@ -79,7 +83,7 @@ def main():
         wall = (time.time() - t0) / (3 * len(views)) * 1e3
         dev_ms = e0.elapsed_time(e1) / (3 * len(views))
         out = {k: round(ms[k] / max(calls["preprocess"], 1), 4) for k in ms}
-        print(json.dumps({"ppt_fwd:bwd": G, "P": P, "V": V, "R": R, "scale": a.scale, "stage_ms": out,
+        print(json.dumps({"ppt_fwd:bwd": G, "tune": tune, "P": P, "V": V, "R": R, "scale": a.scale, "stage_ms": out,
                           "sum_ms": round(sum(out.values()), 4), "ms_per_view_events": round(dev_ms, 4),
                           "ms_per_view_wall": round(wall, 4)}))
 
