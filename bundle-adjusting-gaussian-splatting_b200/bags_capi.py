@@ -59,6 +59,7 @@ SIGNATURES = {
     "bags_center_crop_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "bags_center_crop_backward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "bags_loss_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bags_loss_window": (c_int, [c_void_p]),
     "bags_loss_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_unpack_state": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P,

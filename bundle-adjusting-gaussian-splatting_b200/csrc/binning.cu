@@ -27,7 +27,7 @@ namespace bags {
 // =================================================================================================================
 constexpr size_t SORT_SMEM_BYTES = (2 * SORT_TILE + SORT_WARPS * RADIX + 2 * RADIX + 8) * sizeof(u32);
 constexpr int SORT_LOOKBACK_FIRST = 8;   // predecessor status words fetched in the first look-back round
-static int g_sort_lookback = 32;         // ... and in every later round (8, 16, 32 or 64; see bags_set_tuning)
+static int g_sort_lookback = 8;          // ... and in every later round (4, 8, 16 or 32; see bags_set_tuning)
 constexpr u32 FLAG_AGG = 1u << 30;   // tile aggregate available
 constexpr u32 FLAG_INCL = 2u << 30;  // inclusive prefix available
 constexpr u32 VAL_MASK = (1u << 30) - 1;
@@ -66,17 +66,33 @@ sort_hist_kernel(const u32* __restrict__ keys, int n, int begin_bit, int end_bit
 }
 
 // Lanes of the warp holding the same digit as the caller: one ballot per digit bit (the match.any instruction has a
-// far lower throughput than `bits` votes).
-__device__ __forceinline__ u32 match_digit(const u32 d, const int bits) {
+// far lower throughput than `bits` votes).  Four instructions per bit: bit test into a predicate, vote, select of the
+// polarity mask, one three-input logic op.
+template <int B>
+__device__ __forceinline__ void match_bit(u32& peers, const u32 d) {
+    // peers &= set ? vote : ~vote, spelled out so that ptxas keeps it at four instructions per bit
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, v, f;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+        "selp.b32 f, 0, 0xffffffff, p;\n\t"
+        "lop3.b32 %0, %0, v, f, 0x60;\n\t"
+        "}"
+        : "+r"(peers) : "r"(d), "n"(1u << B));
+}
+template <int BITS>
+__device__ __forceinline__ u32 match_digit_fixed(const u32 d) {
     u32 peers = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < RADIX_BITS; b++) {
-        if (b < bits) {
-            const bool set = (d >> b) & 1u;
-            const u32 vote = __ballot_sync(0xffffffffu, set);
-            peers &= set ? vote : ~vote;
-        }
-    }
+    match_bit<0>(peers, d);
+    if (BITS > 1) match_bit<1>(peers, d);
+    if (BITS > 2) match_bit<2>(peers, d);
+    if (BITS > 3) match_bit<3>(peers, d);
+    if (BITS > 4) match_bit<4>(peers, d);
+    if (BITS > 5) match_bit<5>(peers, d);
+    if (BITS > 6) match_bit<6>(peers, d);
+    if (BITS > 7) match_bit<7>(peers, d);
     return peers;
 }
 
@@ -123,7 +139,51 @@ __device__ __forceinline__ bool lookback_round(const u32* __restrict__ status, c
     return done;
 }
 
-template <bool IOTA, int LOOKBACK>
+// Digit of a key.  BYTE: the digit is one whole byte of the key (8 bits, shift a multiple of 8): one PRMT.
+template <bool BYTE>
+__device__ __forceinline__ u32 digit_of(const u32 key, const int shift, const u32 mask, const u32 sel) {
+    if (BYTE) return __byte_perm(key, 0u, sel);
+    return (key >> shift) & mask;
+}
+
+// Rank of every key of the thread inside its warp's digit groups, in memory order.
+// Per item: the lanes holding the same digit (one ballot per digit bit), the number of them below this lane, and one
+// shared-memory atomic by the leader lane that reserves the group's slots in the warp's digit counter.  The atomics
+// of one warp reach the shared-memory unit in program order, so equal digits of later items see the counts of earlier
+// ones without a warp barrier per item, and groups of items pipeline instead of forming a chain of 16
+// load-add-store-shuffle round trips.  Padding keys (0xFFFFFFFF, only past the end of the last tile) fall into the
+// highest digit after every real key, so they need no special case.
+template <int BITS, bool BYTE>
+__device__ __forceinline__ void rank_items(const u32 (&key)[SORT_ITEMS], u32 (&rank)[SORT_ITEMS], u32* wc,
+                                           const int shift, const u32 mask, const u32 sel, const int lane) {
+    const u32 lt_mask = (1u << lane) - 1u;
+    const u32 wc_addr = (u32)__cvta_generic_to_shared(wc);
+    constexpr int RANK_GROUP = 4;   // items in flight between the atomics and the shuffles that distribute them
+#pragma unroll
+    for (int i0 = 0; i0 < SORT_ITEMS; i0 += RANK_GROUP) {
+        u32 old[RANK_GROUP];
+#pragma unroll
+        for (int k = 0; k < RANK_GROUP; k++) {
+            const int i = i0 + k;
+            const u32 d = digit_of<BYTE>(key[i], shift, mask, sel);
+            const u32 peers = match_digit_fixed<BITS>(d);
+            const u32 lower = __popc(peers & lt_mask);
+            const u32 cnt = __popc(peers);
+            old[k] = 0;
+            // lowest lane of the group leads (predicated atomic: no divergent region)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], %3;\n\t}"
+                         : "+r"(old[k]) : "r"(wc_addr + d * 4u), "r"(lower), "r"(cnt) : "memory");
+            rank[i] = lower | ((u32)(__ffs(peers) - 1) << 16);
+        }
+#pragma unroll
+        for (int k = 0; k < RANK_GROUP; k++) {
+            const int i = i0 + k;
+            rank[i] = __shfl_sync(0xffffffffu, old[k], (int)(rank[i] >> 16)) + (rank[i] & 0xffffu);
+        }
+    }
+}
+
+template <bool IOTA, int LOOKBACK, bool BYTE>
 __global__ void __launch_bounds__(SORT_THREADS, 4)
 onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, u32* __restrict__ keys_out,
                      u32* __restrict__ vals_out, int n, int shift, int bits, const u32* __restrict__ ghist,
@@ -132,9 +192,8 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     u32* s_keys = sort_smem;                                             // [SORT_TILE] keys in locally sorted order
     u32* s_vals = s_keys + SORT_TILE;                                    // [SORT_TILE] their values
     u32 (*s_wcnt)[RADIX] = reinterpret_cast<u32 (*)[RADIX]>(s_vals + SORT_TILE);  // [SORT_WARPS][RADIX]
-    u32* s_local = s_vals + SORT_TILE + SORT_WARPS * RADIX;              // [RADIX] digit offset inside the tile
-    u32* s_gbase = s_local + RADIX;                                      // [RADIX] global index of local position 0
-    u32* s_wtot = s_gbase + RADIX;                                       // [8]
+    u32* s_gbase = s_vals + SORT_TILE + SORT_WARPS * RADIX;              // [RADIX] global index of local position 0
+    u32* s_wtot = s_gbase + 2 * RADIX;                                   // [8]
     __shared__ u32 s_tile;
     static_assert(SORT_THREADS == RADIX, "one thread per digit in the look-back");
 
@@ -145,45 +204,37 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     const u32 tile = s_tile;
     const long long tile_base = (long long)tile * SORT_TILE;
     const int nvalid = (int)min((long long)SORT_TILE, (long long)n - tile_base);
+    const bool full = nvalid == SORT_TILE;                               // CTA-uniform
     const u32 mask = (1u << bits) - 1u;
+    const u32 sel = 0x4440u | (u32)(shift >> 3);
 
     // ---- load keys, warp-striped: item i of lane l of warp w sits at w*512 + i*32 + l ----
     u32 key[SORT_ITEMS];
     u32 rank[SORT_ITEMS];
     const int wbase = warp * (32 * SORT_ITEMS) + lane;
+    const u32* kin = keys_in + tile_base + wbase;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++) {
-        int loc = wbase + i * 32;
-        key[i] = (loc < nvalid) ? keys_in[tile_base + loc] : 0xFFFFFFFFu;
+        for (int i = 0; i < SORT_ITEMS; i++) key[i] = kin[i * 32];
+    } else {
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) key[i] = (wbase + i * 32 < nvalid) ? kin[i * 32] : 0xFFFFFFFFu;
     }
 
     // ---- rank inside the warp, in memory order ----
-    // Per item: the lanes holding the same digit (one ballot per digit bit), the number of them below this lane, and
-    // one shared-memory atomic by the leader lane that reserves the group's slots in the warp's digit counter.  The
-    // atomics of one warp reach the shared-memory unit in program order, so equal digits of later items see the
-    // counts of earlier ones without a warp barrier per item, and groups of items pipeline instead of forming a
-    // chain of 16 load-add-store-shuffle round trips.
-    const u32 lt_mask = (1u << lane) - 1u;
     u32* wc = s_wcnt[warp];
-    constexpr int RANK_GROUP = 4;   // items in flight between the atomics and the shuffles that distribute them
-#pragma unroll
-    for (int i0 = 0; i0 < SORT_ITEMS; i0 += RANK_GROUP) {
-        u32 old[RANK_GROUP];
-#pragma unroll
-        for (int k = 0; k < RANK_GROUP; k++) {
-            const int i = i0 + k;
-            int loc = wbase + i * 32;
-            u32 d = (loc < nvalid) ? ((key[i] >> shift) & mask) : (u32)(RADIX - 1);
-            u32 peers = match_digit(d, bits);
-            u32 lower = __popc(peers & lt_mask);
-            old[k] = 0;
-            if (lower == 0) old[k] = atomicAdd(&wc[d], (u32)__popc(peers));   // lowest lane of the group leads
-            rank[i] = lower | ((u32)(__ffs(peers) - 1) << 8);
-        }
-#pragma unroll
-        for (int k = 0; k < RANK_GROUP; k++) {
-            const int i = i0 + k;
-            rank[i] = __shfl_sync(0xffffffffu, old[k], (int)(rank[i] >> 8)) + (rank[i] & 0xffu);
+    if (BYTE) {
+        rank_items<8, true>(key, rank, wc, shift, mask, sel, lane);
+    } else {
+        switch (bits) {   // CTA-uniform
+            case 8: rank_items<8, false>(key, rank, wc, shift, mask, sel, lane); break;
+            case 7: rank_items<7, false>(key, rank, wc, shift, mask, sel, lane); break;
+            case 6: rank_items<6, false>(key, rank, wc, shift, mask, sel, lane); break;
+            case 5: rank_items<5, false>(key, rank, wc, shift, mask, sel, lane); break;
+            case 4: rank_items<4, false>(key, rank, wc, shift, mask, sel, lane); break;
+            case 3: rank_items<3, false>(key, rank, wc, shift, mask, sel, lane); break;
+            case 2: rank_items<2, false>(key, rank, wc, shift, mask, sel, lane); break;
+            default: rank_items<1, false>(key, rank, wc, shift, mask, sel, lane); break;
         }
     }
     __syncthreads();
@@ -202,11 +253,10 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
         if (tile > 0) {
             st_volatile_u32(st, sum | FLAG_AGG);
             // Decoupled look-back, several predecessors per round: the loads of a round are independent, so a walk
-            // over k tiles costs about k / LOOKBACK memory round trips instead of k.  When a whole wave of CTAs
-            // publishes its aggregates at the same time, the front of inclusive prefixes advances LOOKBACK tiles per
-            // round trip and tile k resolves after about k / (2 LOOKBACK) of them: with 8 words per round that chain
-            // (~600 resident tiles) was most of a pass's duration.  The first round stays short for the common late
-            // case (the nearest predecessors already hold inclusive prefixes).
+            // over k tiles costs about k / LOOKBACK memory round trips instead of k.  Measured on B200 (C3, per-view
+            // depth sort / tile sort, us): 8 words -> 83 / 118, 16 -> 90 / 122, 32 -> 97 / 131, 64 -> 122 / 164:
+            // beyond 8 the extra status traffic costs more than the shorter chain saves (the passes are
+            // instruction-issue bound, not chain bound), so 8 is the default.
             int look = (int)tile - 1;
             bool done = lookback_round<SORT_LOOKBACK_FIRST>(status, tid, look, excl);
             while (!done) done = lookback_round<LOOKBACK>(status, tid, look, excl);
@@ -216,30 +266,35 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
         u32 local_excl = block_excl_scan_256(sum, s_wtot, tid);
         u32 gh = ghist[tid];
         u32 gexcl = block_excl_scan_256(gh, s_wtot, tid);
-        s_local[tid] = local_excl;
         s_gbase[tid] = gexcl + excl - local_excl;
+        // fold the digit's offset inside the tile into the per-warp offsets: one table lookup per key below
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) s_wcnt[w][tid] += local_excl;
     }
     __syncthreads();
 
     // ---- scatter keys and values to their locally sorted position, then write coalesced runs ----
+    {
+        const u32* vin = vals_in + tile_base + wbase;
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++) {
-        int loc = wbase + i * 32;
-        u32 d = (loc < nvalid) ? ((key[i] >> shift) & mask) : (u32)(RADIX - 1);
-        u32 pos = s_local[d] + wc[d] + rank[i];
-        u32 v = 0;
-        if (loc < nvalid) v = IOTA ? (u32)(tile_base + loc) : vals_in[tile_base + loc];
-        s_keys[pos] = key[i];
-        s_vals[pos] = v;
+        for (int i = 0; i < SORT_ITEMS; i++) {
+            const u32 d = digit_of<BYTE>(key[i], shift, mask, sel);
+            const u32 pos = wc[d] + rank[i];
+            u32 v;
+            if (IOTA) v = (u32)(tile_base + wbase + i * 32);
+            else if (full) v = vin[i * 32];
+            else v = (wbase + i * 32 < nvalid) ? vin[i * 32] : 0u;
+            s_keys[pos] = key[i];
+            s_vals[pos] = v;
+        }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
-        int p = i * SORT_THREADS + tid;
-        if (p < nvalid) {
-            u32 k = s_keys[p];
-            u32 d = (k >> shift) & mask;
-            u32 dst = s_gbase[d] + (u32)p;
+        const int p = i * SORT_THREADS + tid;
+        if (full || p < nvalid) {
+            const u32 k = s_keys[p];
+            const u32 dst = s_gbase[digit_of<BYTE>(k, shift, mask, sel)] + (u32)p;
             keys_out[dst] = k;
             vals_out[dst] = s_vals[p];
         }
@@ -274,22 +329,25 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
         const bool iota = p == 0 && iota_vals;
         // the shared-memory attribute is per device; setting it is a cheap driver call, so do it on every launch
         // (multi-device safe)
-#define BAGS_PASS(IOTA, LB)                                                                                        \
+        const bool byte_digit = bits == 8 && (sft & 7) == 0;
+#define BAGS_PASS(IOTA, LB, BYTE)                                                                                  \
     do {                                                                                                           \
-        BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB>,                                          \
+        BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB, BYTE>,                                    \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_BYTES));     \
-        onesweep_pass_kernel<IOTA, LB><<<ntiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(                             \
+        onesweep_pass_kernel<IOTA, LB, BYTE><<<ntiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(                       \
             ki, vi, ko, vo, n, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status);                      \
     } while (0)
 #define BAGS_PASS_LB(LB)                                                                                           \
     do {                                                                                                           \
-        if (iota) BAGS_PASS(true, LB);                                                                             \
-        else BAGS_PASS(false, LB);                                                                                 \
+        if (iota && byte_digit) BAGS_PASS(true, LB, true);                                                         \
+        else if (iota) BAGS_PASS(true, LB, false);                                                                 \
+        else if (byte_digit) BAGS_PASS(false, LB, true);                                                           \
+        else BAGS_PASS(false, LB, false);                                                                          \
     } while (0)
-        if (g_sort_lookback == 8) BAGS_PASS_LB(8);
+        if (g_sort_lookback == 4) BAGS_PASS_LB(4);
         else if (g_sort_lookback == 16) BAGS_PASS_LB(16);
-        else if (g_sort_lookback == 64) BAGS_PASS_LB(64);
-        else BAGS_PASS_LB(32);
+        else if (g_sort_lookback == 32) BAGS_PASS_LB(32);
+        else BAGS_PASS_LB(8);
 #undef BAGS_PASS_LB
 #undef BAGS_PASS
         BAGS_LAUNCH_OK("onesweep_pass_kernel");
@@ -514,7 +572,7 @@ int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cuda
 
 int set_sort_lookback(int value) {
     const int prev = g_sort_lookback;
-    if (value == 8 || value == 16 || value == 32 || value == 64) g_sort_lookback = value;
+    if (value == 4 || value == 8 || value == 16 || value == 32) g_sort_lookback = value;
     return prev;
 }
 

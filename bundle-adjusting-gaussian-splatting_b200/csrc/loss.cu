@@ -31,15 +31,20 @@ constexpr int LTHREADS = 256;
 struct LossWindow { float g[LW]; };
 
 // loss_utils.py:36-38: gauss = Tensor([exp(-(x - 5)^2 / (2 * 1.5^2))]) / sum, evaluated in double by Python and
-// rounded to fp32 by torch.Tensor, summed and divided in fp32.
+// rounded to fp32 by torch.Tensor, then divided in fp32 by gauss.sum().  torch's CPU sum of the 11 values is a
+// multi-accumulator reduction whose result equals the correctly rounded sum; a left-to-right fp32 loop lands one ulp
+// lower, which scales every weight by 1 + 6e-8 and -- because sigma12 = E[xy] - mu1 mu2 is a difference of nearly
+// equal numbers -- biased the mean SSIM of smooth 1080p images by 1.2e-5.  The sum is therefore formed in double and
+// rounded once.
 static LossWindow make_window() {
     LossWindow w;
-    float s = 0.f;
+    double s = 0.0;
     for (int x = 0; x < LW; x++) {
         w.g[x] = (float)exp(-(double)((x - LW / 2) * (x - LW / 2)) / (2.0 * 1.5 * 1.5));
-        s += w.g[x];
+        s += (double)w.g[x];
     }
-    for (int x = 0; x < LW; x++) w.g[x] = w.g[x] / s;
+    const float sf = (float)s;
+    for (int x = 0; x < LW; x++) w.g[x] = w.g[x] / sf;
     return w;
 }
 
@@ -243,6 +248,16 @@ static inline int loss_blocks(int H, int W) { return ((W + LT - 1) / LT) * ((H +
 }  // namespace bags
 
 using namespace bags;
+
+extern "C" int bags_loss_window(float* taps11) {
+    if (!taps11) {
+        set_error("bags_loss_window: null output");
+        return BAGS_E_INVALID;
+    }
+    const LossWindow w = make_window();
+    for (int x = 0; x < LW; x++) taps11[x] = w.g[x];
+    return 0;
+}
 
 extern "C" size_t bags_loss_scratch_bytes(int planes, int H, int W) {
     if (planes < 0 || H < 0 || W < 0) return 0;

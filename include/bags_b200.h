@@ -235,6 +235,10 @@ int bags_center_crop_backward(const float* dL_dout, int C, int H, int W, int Hc,
  * Backward: dL_dimg1 = coef[plane][0] * d(sum|.|)/dimg1 + coef[plane][1] * d(sum ssim_map)/dimg1, with coef a DEVICE
  * array [planes][2] (the upstream gradients never visit the host).  Pass NULL maps for an L1-only backward. */
 size_t bags_loss_scratch_bytes(int planes, int H, int W);
+/* The 11 fp32 taps of the 1-D Gaussian window the loss kernels use (host memory; no device work).  They must equal
+ * utils/loss_utils.py:36-38 `gauss / gauss.sum()` bit for bit: a one-ulp difference in the normaliser biases the mean
+ * SSIM of smooth images by 1e-5 (tests/test_host_logic.py pins them against torch). */
+int bags_loss_window(float* taps11);
 int bags_loss_forward(const float* img1, const float* img2, int planes, int H, int W, int want_ssim, float* d_mu1,
                       float* d_e11, float* d_e12, char* scratch, double* sums, void* stream);
 int bags_loss_backward(const float* img1, const float* img2, int planes, int H, int W, const float* d_mu1,
@@ -277,7 +281,7 @@ int bags_profile_read(double* ms, unsigned long long* calls);
  * summation order of the gradients.  BLEND_CULL: 1 (default) skips, per 8x4 patch, the splats whose alpha >= 1/255
  * bounding box misses the patch; 0 evaluates every splat of the tile list for every patch (must give the same forward
  * bits -- used by the tests).  SORT_LOOKBACK: predecessor status words the onesweep passes fetch per look-back
- * round (8, 16, 32 or 64; default 32; no effect on results).  Returns the previous value (other values only
+ * round (4, 8, 16 or 32; default 8; no effect on results).  Returns the previous value (other values only
  * query), BAGS_E_INVALID for an unknown knob. */
 enum { BAGS_TUNE_BLEND_FWD_PPT = 0, BAGS_TUNE_BLEND_BWD_PPT = 1, BAGS_TUNE_BLEND_CULL = 2,
        BAGS_TUNE_SORT_LOOKBACK = 3 };

@@ -119,3 +119,17 @@ def test_synthetic_scene_is_deterministic():
     assert torch.allclose(inv[3, :3].float(), cam.campos, atol=1e-6)
     V, R = S.estimate_tile_instances(a, cam)
     assert 0 < V <= 500 and R >= V
+
+
+def test_loss_window_taps_equal_reference_window():
+    """utils/loss_utils.py:36-38: the kernels' 11 taps must be the reference's `gauss / gauss.sum()` bit for bit (the
+    normaliser is torch's fp32 sum, which equals the correctly rounded sum; one ulp off biases SSIM by 1e-5)."""
+    import ctypes
+    import math
+    import bags_capi
+    taps = (ctypes.c_float * 11)()
+    assert bags_capi.lib().bags_loss_window(ctypes.cast(taps, ctypes.c_void_p)) == 0
+    gauss = torch.Tensor([math.exp(-(x - 11 // 2) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+    want = gauss / gauss.sum()
+    got = torch.tensor(list(taps), dtype=torch.float32)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))

@@ -217,12 +217,15 @@ def test_onesweep_sort_matches_stable_sort():
     L = capi.lib()
     d = dev()
     for n, (b0, b1) in [(0, (0, 32)), (1, (0, 32)), (777, (0, 32)), (8192, (0, 13)), (8193, (0, 32)),
-                        (300001, (0, 32)), (1_000_000, (3, 17)), (3_000_000, (0, 15))]:
+                        (300001, (0, 32)), (1_000_000, (3, 17)), (3_000_000, (0, 15)), (50_000, (5, 8)),
+                        (12288, (8, 32)), (100_001, (0, 1)), (70_000, (2, 13)), (4097, (16, 22)),
+                        (200_000, (7, 11))]:
         g = torch.Generator().manual_seed(n + 1)
-        keys = torch.randint(0, 2 ** 31 - 1, (max(n, 1),), generator=g, dtype=torch.int64)[:n]
+        keys = torch.randint(0, 2 ** 32, (max(n, 1),), generator=g, dtype=torch.int64)[:n]   # all 32 bits in use
         if n > 1000:
             keys[: n // 2] = keys[: n // 2] & 0x3FF
-        keys = keys.to(torch.int32).to(d)
+        keys_u = keys.clone()
+        keys = torch.where(keys >= 2 ** 31, keys - 2 ** 32, keys).to(torch.int32).to(d)
         vals = torch.arange(n, dtype=torch.int32, device=d)
         ko, vo = torch.empty_like(keys), torch.empty_like(vals)
         scratch = torch.empty(int(L.bags_sort_scratch_bytes(n)), dtype=torch.uint8, device=d)
@@ -233,7 +236,7 @@ def test_onesweep_sort_matches_stable_sort():
         torch.cuda.synchronize()
         if n == 0:
             continue
-        kk = (keys.to(torch.int64) >> b0) & ((1 << (b1 - b0)) - 1)
+        kk = ((keys_u >> b0) & ((1 << (b1 - b0)) - 1)).to(d)
         order = torch.sort(kk, stable=True).indices
         assert torch.equal(vo.to(torch.int64), order)
         assert torch.equal(ko, keys[order])
