@@ -100,3 +100,77 @@ def run_views(params: FlatGaussianParams, views: Sequence, view_loss: Callable, 
         losses.append(loss.detach())
     allreduce_gradients(params, group)
     return losses
+
+
+class ViewStreams:
+    """Software pipelining of a rank's views over a few CUDA streams (several views
+    over the same Gaussians in flight at once).
+
+    A view's preprocess + binning kernels are short and latency bound (they fill a fraction of the GPU), its blend
+    kernels are long and issue bound.  Issuing consecutive views on alternating streams lets view k's preprocess /
+    binning / forward blend run underneath view k-1's backward.  The backward passes themselves are chained with
+    events (view k's backward starts after view k-1's has finished): they all add into the same flat gradient buffer,
+    and two issue-bound backward kernels gain nothing from running side by side.
+
+        vs = ViewStreams(device, depth=2)
+        vs.begin()                         # after params.zero_grad(), on the current stream
+        for k, view in enumerate(views):
+            with vs.view(k):
+                outputs = render(view)
+                vs.before_backward()
+                torch.autograd.backward(outputs, grads)
+                vs.after_backward()
+        vs.end()                           # the current stream waits for every view
+    """
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.depth = max(1, int(depth))
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)] if self.depth > 1 else []
+        self._last_bwd = None
+        self._cur = None
+        self._ctx = None
+
+    def begin(self):
+        self._last_bwd = None
+        if self.depth > 1:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            for s in self.streams:
+                s.wait_event(ev)
+
+    def view(self, k: int):
+        vs = self
+
+        class _Scope:
+            def __enter__(self_inner):
+                if vs.depth > 1:
+                    vs._cur = vs.streams[k % vs.depth]
+                    vs._ctx = torch.cuda.stream(vs._cur)
+                    vs._ctx.__enter__()
+                return vs
+
+            def __exit__(self_inner, *exc):
+                if vs.depth > 1:
+                    vs._ctx.__exit__(*exc)
+                    vs._cur = None
+                return False
+        return _Scope()
+
+    def before_backward(self):
+        if self.depth > 1 and self._last_bwd is not None:
+            self._cur.wait_event(self._last_bwd)
+
+    def after_backward(self):
+        if self.depth > 1:
+            ev = torch.cuda.Event()
+            ev.record(self._cur)
+            self._last_bwd = ev
+
+    def end(self):
+        if self.depth > 1:
+            main = torch.cuda.current_stream(self.device)
+            for s in self.streams:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                main.wait_event(ev)

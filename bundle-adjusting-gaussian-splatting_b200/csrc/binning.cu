@@ -322,18 +322,23 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
     const int ntiles = (n + SORT_TILE - 1) / SORT_TILE;
     // per-device attribute; setting it is a cheap driver call, so do it on every sort (multi-device safe)
     u32 *ki = keys_in, *vi = vals_in, *ko = keys_out, *vo = vals_out;
+    int cur_dev = 0;
+    BAGS_CUDA_OK(cudaGetDevice(&cur_dev));
     for (int p = 0; p < npass; p++) {
         int sft = begin_bit + p * RADIX_BITS;
         int bits = min(RADIX_BITS, end_bit - sft);
         u32* status = sc.status + (size_t)p * sc.ntiles * RADIX;
         const bool iota = p == 0 && iota_vals;
-        // the shared-memory attribute is per device; setting it is a cheap driver call, so do it on every launch
-        // (multi-device safe)
+        // the shared-memory attribute is per device and per kernel: set once for each
         const bool byte_digit = bits == 8 && (sft & 7) == 0;
 #define BAGS_PASS(IOTA, LB, BYTE)                                                                                  \
     do {                                                                                                           \
-        BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB, BYTE>,                                    \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_BYTES));     \
+        static bool attr_set[64] = {};   /* per kernel variant (expansion site) and device */                      \
+        if (!attr_set[cur_dev & 63]) {                                                                             \
+            BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB, BYTE>,                                \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_BYTES)); \
+            attr_set[cur_dev & 63] = true;                                                                         \
+        }                                                                                                          \
         onesweep_pass_kernel<IOTA, LB, BYTE><<<ntiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(                       \
             ki, vi, ko, vo, n, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status);                      \
     } while (0)

@@ -97,6 +97,14 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
 
     if (idx < P) {
         p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+        // scale / rotation are fetched together with the mean (before the cull decision and the projection math):
+        // one memory round trip instead of two on the critical path of every warp; 5% of the rows are culled
+        float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        if (!HAS_COV) {
+            sc0 = scales[3 * idx]; sc1 = scales[3 * idx + 1]; sc2 = scales[3 * idx + 2];
+            q0 = rotations[4 * idx]; q1 = rotations[4 * idx + 1]; q2 = rotations[4 * idx + 2];
+            q3 = rotations[4 * idx + 3];
+        }
         const float3 p_view = xform4x3(p_orig, vm);
 
         // Near-plane culling only (auxiliary.h:154).
@@ -128,9 +136,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
 #pragma unroll
                 for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * idx + k];
             } else {
-                cov3d_from_scale_rot(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2], scale_modifier,
-                                     rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2],
-                                     rotations[4 * idx + 3], cov6);
+                cov3d_from_scale_rot(sc0, sc1, sc2, scale_modifier, q0, q1, q2, q3, cov6);
             }
 
             // EWA 2D covariance, forward.cu:99-164 (t.z carries the pupil shift).

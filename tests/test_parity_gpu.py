@@ -475,3 +475,67 @@ def test_gradient_sink_rejects_bad_buffers():
         mod.register_grad_sink(p, torch.zeros(10, 3, device=d, dtype=torch.float64))
     with pytest.raises(RuntimeError):
         mod.register_grad_sink(p.detach().cpu().requires_grad_(True), torch.zeros(10, 3))
+
+
+@pytest.mark.parametrize("sinks", [True, False])
+def test_view_streams_pipeline_equals_serial(sinks):
+    """bags_view_parallel.ViewStreams: four views pipelined over two CUDA streams (view k's forward under view k-1's
+    backward) give the gradients and images of the same views run one after the other on one stream."""
+    import bags_view_parallel as VP
+    mod = pc.load_ours()
+    d = dev()
+    W, H, P = 320, 208, 20000
+    cam0 = S.make_camera(W, H, seed=100)
+    gs = S.make_gaussians(P, cam0, seed=0, scale=0.02)
+    cams = [S.make_camera(W, H, seed=100 + v) for v in range(4)]
+    ups = [[u.to(d) for u in S.make_upstream(H, W, seed=1 + v)] for v in range(4)]
+
+    def run(depth):
+        params = VP.FlatGaussianParams(gs.means3D.to(d), gs.shs.to(d), gs.opacities.to(d), gs.scales.to(d),
+                                       gs.rotations.to(d), device=d)
+        if sinks:
+            params.enable_direct_accumulation(mod)
+        shift = torch.zeros(3, device=d, requires_grad=True)
+        pipe = VP.ViewStreams(d, depth=depth)
+        images, pose = [], []
+        try:
+            for rep in range(2):        # twice: the second round reuses streams, events and cached blocks
+                params.zero_grad()
+                images, leaves = [], []
+                pipe.begin()
+                for k, (cam, up) in enumerate(zip(cams, ups)):
+                    view = cam.viewmatrix.to(d).requires_grad_(True)
+                    proj = cam.projmatrix.to(d).requires_grad_(True)
+                    campos = cam.campos.to(d).requires_grad_(True)
+                    leaves.append((view, proj, campos))
+                    st = mod.GaussianRasterizationSettings(
+                        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                        bg=torch.zeros(3, device=d), scale_modifier=1.0, viewmatrix=view, projmatrix=proj,
+                        intrinsic=cam.intrinsic.to(d), sh_degree=3, campos=campos, prefiltered=False, debug=False,
+                        debug_iter=0)
+                    with pipe.view(k):
+                        m2d = torch.zeros_like(params["means3D"], requires_grad=True)
+                        m2dd = torch.zeros_like(params["means3D"], requires_grad=True)
+                        color, radii, depth_img, weights, _ = mod.GaussianRasterizer(raster_settings=st)(
+                            means3D=params["means3D"], means2D=m2d, means2D_densify=m2dd, shift_factors=shift,
+                            opacities=params["opacities"], shs=params["shs"], scales=params["scales"],
+                            rotations=params["rotations"])
+                        pipe.before_backward()
+                        torch.autograd.backward([color, depth_img, weights], up)
+                        pipe.after_backward()
+                        images.append(color.detach())
+                pipe.end()
+                torch.cuda.synchronize()
+                pose = [torch.cat([v.grad.flatten(), p.grad.flatten(), c.grad]).cpu() for v, p, c in leaves]
+        finally:
+            params.disable_direct_accumulation()
+        return params.flat_grad.cpu(), [i.cpu() for i in images], pose
+
+    g1, img1, pose1 = run(1)
+    g2, img2, pose2 = run(2)
+    assert pc.rel_l2(g2, g1) <= 1e-5
+    assert float(g1.abs().max()) > 0
+    for a, b in zip(img2, img1):
+        assert torch.equal(a, b)                      # the forward is deterministic
+    for a, b in zip(pose2, pose1):
+        assert pc.rel_l2(a, b) <= 1e-5
