@@ -8,9 +8,9 @@ Contract (see DESIGN.md "Measurement"): a step = one training iteration over `vi
 Gaussian-parameter gradients accumulate in one flat buffer and (N>1) are summed with one NCCL all-reduce.
 `value` = views/s with the upstream image gradients resident in HBM; `e2e` = the same through host buffers: each
 view's 8-bit ground-truth image comes from pinned host memory (H2D on a copy stream, prefetched one view ahead), is
-converted to fp32 on the device, the L1 loss (ours: bags_loss.l1_loss, the drop-in for utils/loss_utils.py; reference
-arm: the torch operator sequence of utils/loss_utils.py:18-19) is computed on the device and read back (D2H) inside
-the timed region.  Prints ONE JSON line on rank 0.
+converted to fp32 on the device, the L1 loss (the torch operator sequence of utils/loss_utils.py:18-19 in both arms;
+--fused-loss switches ours to bags_loss.l1_loss) is computed on the device and read back (D2H) inside the timed
+region.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -51,8 +51,9 @@ def parse():
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the views of a step are pipelined over (bags_view_parallel.ViewStreams): view "
                          "k's preprocess/binning/forward overlaps view k-1's backward; 1 = everything on one stream")
-    ap.add_argument("--torch-loss", action="store_true",
-                    help="e2e leg: L1 loss as torch operators (what the reference arm runs) instead of bags_loss")
+    ap.add_argument("--fused-loss", action="store_true",
+                    help="e2e leg: bags_loss.l1_loss (fused kernels) instead of the torch operator sequence of "
+                         "utils/loss_utils.py:18-19 that both arms run by default")
     ap.add_argument("--trace", default="", help="development: write a GPU timeline summary of 2 device-leg and 2 "
                                                 "e2e steps (torch.profiler) to this JSON file; not a bench value")
     return ap.parse_args()
@@ -295,7 +296,7 @@ def main():
             VP.allreduce_gradients(params)
 
     copy_stream = torch.cuda.Stream(device=dev)
-    if args.impl == "ours" and not args.torch_loss:
+    if args.impl == "ours" and args.fused_loss:
         import bags_loss          # drop-in for utils/loss_utils.py:l1_loss (fused forward/backward kernels)
         l1_loss = bags_loss.l1_loss
     else:
@@ -396,8 +397,14 @@ def main():
         import bags_capi as capi
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    # W untimed warm-up steps, and at least ~1.5 s of them: the first timed region of a run was measured 5-90% slower
+    # than the following ones with only a handful of warm-up steps (allocator growth, clocks, page-locked staging)
+    t_warm, n_warm = time.time(), 0
+    while n_warm < max(args.warmup, 3) or (time.time() - t_warm < 1.5 and n_warm < 400):
         step_device()
+        n_warm += 1
+        if n_warm % 8 == 0:
+            torch.cuda.synchronize()
     barrier()
     if sampler is not None:
         sampler.wait_first_sample()
@@ -422,7 +429,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        for _ in range(2):
+        for _ in range(max(args.warmup, 3)):
             step_e2e()
         finish_e2e()
         ms_e2e, ms_e2e_all = timed(step_e2e, args.steps, finish_e2e)

@@ -25,9 +25,13 @@ namespace bags {
 // Onesweep radix sort (u32 keys, u32 values), 8-bit digits, one CTA per 4096-key tile (4 CTAs per SM), decoupled
 // look-back with several predecessors in flight per round.
 // =================================================================================================================
-constexpr size_t SORT_SMEM_BYTES = (2 * SORT_TILE + SORT_WARPS * RADIX + 2 * RADIX + 8) * sizeof(u32);
+constexpr size_t sort_smem_bytes(int items) {
+    return (size_t)(2 * items * SORT_THREADS + SORT_WARPS * RADIX + 2 * RADIX + 8) * sizeof(u32);
+}
 constexpr int SORT_LOOKBACK_FIRST = 8;   // predecessor status words fetched in the first look-back round
-static int g_sort_lookback = 8;          // ... and in every later round (4, 8, 16 or 32; see bags_set_tuning)
+static int g_sort_small_tiles = 1;       // 2048-key tiles for passes that do not fill the GPU twice (see launch_sort_pairs)
+static int g_sort_hwmatch = 0;           // MATCH.ANY ranking in those small-tile passes
+static int g_sort_lookback = 4;          // ... and in every later round (4 or 8; see bags_set_tuning)
 constexpr u32 FLAG_AGG = 1u << 30;   // tile aggregate available
 constexpr u32 FLAG_INCL = 2u << 30;  // inclusive prefix available
 constexpr u32 VAL_MASK = (1u << 30) - 1;
@@ -153,20 +157,22 @@ __device__ __forceinline__ u32 digit_of(const u32 key, const int shift, const u3
 // ones without a warp barrier per item, and groups of items pipeline instead of forming a chain of 16
 // load-add-store-shuffle round trips.  Padding keys (0xFFFFFFFF, only past the end of the last tile) fall into the
 // highest digit after every real key, so they need no special case.
-template <int BITS, bool BYTE>
-__device__ __forceinline__ void rank_items(const u32 (&key)[SORT_ITEMS], u32 (&rank)[SORT_ITEMS], u32* wc,
+template <int BITS, bool BYTE, int ITEMS, bool HWMATCH>
+__device__ __forceinline__ void rank_items(const u32 (&key)[ITEMS], u32 (&rank)[ITEMS], u32* wc,
                                            const int shift, const u32 mask, const u32 sel, const int lane) {
     const u32 lt_mask = (1u << lane) - 1u;
     const u32 wc_addr = (u32)__cvta_generic_to_shared(wc);
     constexpr int RANK_GROUP = 4;   // items in flight between the atomics and the shuffles that distribute them
 #pragma unroll
-    for (int i0 = 0; i0 < SORT_ITEMS; i0 += RANK_GROUP) {
+    for (int i0 = 0; i0 < ITEMS; i0 += RANK_GROUP) {
         u32 old[RANK_GROUP];
 #pragma unroll
         for (int k = 0; k < RANK_GROUP; k++) {
             const int i = i0 + k;
             const u32 d = digit_of<BYTE>(key[i], shift, mask, sel);
-            const u32 peers = match_digit_fixed<BITS>(d);
+            // HWMATCH: one MATCH.ANY instead of BITS votes -- far lower throughput, but a single instruction with no
+            // predicate registers, so the items of a group overlap; only offered to the latency-bound small tiles
+            const u32 peers = HWMATCH ? __match_any_sync(0xffffffffu, d) : match_digit_fixed<BITS>(d);
             const u32 lower = __popc(peers & lt_mask);
             const u32 cnt = __popc(peers);
             old[k] = 0;
@@ -183,16 +189,17 @@ __device__ __forceinline__ void rank_items(const u32 (&key)[SORT_ITEMS], u32 (&r
     }
 }
 
-template <bool IOTA, int LOOKBACK, bool BYTE>
+template <bool IOTA, int LOOKBACK, bool BYTE, int ITEMS, bool HWMATCH>
 __global__ void __launch_bounds__(SORT_THREADS, 4)
 onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, u32* __restrict__ keys_out,
                      u32* __restrict__ vals_out, int n, int shift, int bits, const u32* __restrict__ ghist,
                      u32* __restrict__ tile_counter, u32* __restrict__ status) {
+    constexpr int TILE = ITEMS * SORT_THREADS;
     extern __shared__ u32 sort_smem[];
-    u32* s_keys = sort_smem;                                             // [SORT_TILE] keys in locally sorted order
-    u32* s_vals = s_keys + SORT_TILE;                                    // [SORT_TILE] their values
-    u32 (*s_wcnt)[RADIX] = reinterpret_cast<u32 (*)[RADIX]>(s_vals + SORT_TILE);  // [SORT_WARPS][RADIX]
-    u32* s_gbase = s_vals + SORT_TILE + SORT_WARPS * RADIX;              // [RADIX] global index of local position 0
+    u32* s_keys = sort_smem;                                             // [TILE] keys in locally sorted order
+    u32* s_vals = s_keys + TILE;                                    // [TILE] their values
+    u32 (*s_wcnt)[RADIX] = reinterpret_cast<u32 (*)[RADIX]>(s_vals + TILE);  // [SORT_WARPS][RADIX]
+    u32* s_gbase = s_vals + TILE + SORT_WARPS * RADIX;              // [RADIX] global index of local position 0
     u32* s_wtot = s_gbase + 2 * RADIX;                                   // [8]
     __shared__ u32 s_tile;
     static_assert(SORT_THREADS == RADIX, "one thread per digit in the look-back");
@@ -202,39 +209,39 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_wcnt[0][0])[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
-    const long long tile_base = (long long)tile * SORT_TILE;
-    const int nvalid = (int)min((long long)SORT_TILE, (long long)n - tile_base);
-    const bool full = nvalid == SORT_TILE;                               // CTA-uniform
+    const long long tile_base = (long long)tile * TILE;
+    const int nvalid = (int)min((long long)TILE, (long long)n - tile_base);
+    const bool full = nvalid == TILE;                               // CTA-uniform
     const u32 mask = (1u << bits) - 1u;
     const u32 sel = 0x4440u | (u32)(shift >> 3);
 
     // ---- load keys, warp-striped: item i of lane l of warp w sits at w*512 + i*32 + l ----
-    u32 key[SORT_ITEMS];
-    u32 rank[SORT_ITEMS];
-    const int wbase = warp * (32 * SORT_ITEMS) + lane;
+    u32 key[ITEMS];
+    u32 rank[ITEMS];
+    const int wbase = warp * (32 * ITEMS) + lane;   // item i of lane l of warp w sits at w*32*ITEMS + i*32 + l
     const u32* kin = keys_in + tile_base + wbase;
     if (full) {
 #pragma unroll
-        for (int i = 0; i < SORT_ITEMS; i++) key[i] = kin[i * 32];
+        for (int i = 0; i < ITEMS; i++) key[i] = kin[i * 32];
     } else {
 #pragma unroll
-        for (int i = 0; i < SORT_ITEMS; i++) key[i] = (wbase + i * 32 < nvalid) ? kin[i * 32] : 0xFFFFFFFFu;
+        for (int i = 0; i < ITEMS; i++) key[i] = (wbase + i * 32 < nvalid) ? kin[i * 32] : 0xFFFFFFFFu;
     }
 
     // ---- rank inside the warp, in memory order ----
     u32* wc = s_wcnt[warp];
     if (BYTE) {
-        rank_items<8, true>(key, rank, wc, shift, mask, sel, lane);
+        rank_items<8, true, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane);
     } else {
         switch (bits) {   // CTA-uniform
-            case 8: rank_items<8, false>(key, rank, wc, shift, mask, sel, lane); break;
-            case 7: rank_items<7, false>(key, rank, wc, shift, mask, sel, lane); break;
-            case 6: rank_items<6, false>(key, rank, wc, shift, mask, sel, lane); break;
-            case 5: rank_items<5, false>(key, rank, wc, shift, mask, sel, lane); break;
-            case 4: rank_items<4, false>(key, rank, wc, shift, mask, sel, lane); break;
-            case 3: rank_items<3, false>(key, rank, wc, shift, mask, sel, lane); break;
-            case 2: rank_items<2, false>(key, rank, wc, shift, mask, sel, lane); break;
-            default: rank_items<1, false>(key, rank, wc, shift, mask, sel, lane); break;
+            case 8: rank_items<8, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
+            case 7: rank_items<7, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
+            case 6: rank_items<6, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
+            case 5: rank_items<5, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
+            case 4: rank_items<4, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
+            case 3: rank_items<3, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
+            case 2: rank_items<2, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
+            default: rank_items<1, false, ITEMS, HWMATCH>(key, rank, wc, shift, mask, sel, lane); break;
         }
     }
     __syncthreads();
@@ -255,8 +262,8 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
             // Decoupled look-back, several predecessors per round: the loads of a round are independent, so a walk
             // over k tiles costs about k / LOOKBACK memory round trips instead of k.  Measured on B200 (C3, per-view
             // depth sort / tile sort, us): 8 words -> 83 / 118, 16 -> 90 / 122, 32 -> 97 / 131, 64 -> 122 / 164:
-            // beyond 8 the extra status traffic costs more than the shorter chain saves (the passes are
-            // instruction-issue bound, not chain bound), so 8 is the default.
+            // the wider rounds spill (64-register cap) and the passes are bound by their instruction stream, not by
+            // the chain; 4 words measured another 2-5% faster than 8 and is the default.
             int look = (int)tile - 1;
             bool done = lookback_round<SORT_LOOKBACK_FIRST>(status, tid, look, excl);
             while (!done) done = lookback_round<LOOKBACK>(status, tid, look, excl);
@@ -277,7 +284,7 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     {
         const u32* vin = vals_in + tile_base + wbase;
 #pragma unroll
-        for (int i = 0; i < SORT_ITEMS; i++) {
+        for (int i = 0; i < ITEMS; i++) {
             const u32 d = digit_of<BYTE>(key[i], shift, mask, sel);
             const u32 pos = wc[d] + rank[i];
             u32 v;
@@ -290,7 +297,7 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const int p = i * SORT_THREADS + tid;
         if (full || p < nvalid) {
             const u32 k = s_keys[p];
@@ -319,8 +326,11 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
     int hist_blocks = min((n + 512 * 8 - 1) / (512 * 8), 148 * 4);
     sort_hist_kernel<<<hist_blocks, 512, 0, st>>>(keys_in, n, begin_bit, end_bit, sc.ghist);
     BAGS_LAUNCH_OK("sort_hist_kernel");
-    const int ntiles = (n + SORT_TILE - 1) / SORT_TILE;
-    // per-device attribute; setting it is a cheap driver call, so do it on every sort (multi-device safe)
+    // Keys per CTA: 4096 when the pass runs in several waves (throughput bound), 2048 when even that leaves the GPU
+    // under-filled -- a pass over 1 M keys is bounded by the latency of one CTA's instruction stream, which halves.
+    const bool small = g_sort_small_tiles && (n + SORT_TILE - 1) / SORT_TILE < 2 * 148;
+    const int tile_keys = small ? SORT_TILE_SMALL : SORT_TILE;
+    const int ntiles = (n + tile_keys - 1) / tile_keys;
     u32 *ki = keys_in, *vi = vals_in, *ko = keys_out, *vo = vals_out;
     int cur_dev = 0;
     BAGS_CUDA_OK(cudaGetDevice(&cur_dev));
@@ -329,31 +339,37 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
         int bits = min(RADIX_BITS, end_bit - sft);
         u32* status = sc.status + (size_t)p * sc.ntiles * RADIX;
         const bool iota = p == 0 && iota_vals;
-        // the shared-memory attribute is per device and per kernel: set once for each
         const bool byte_digit = bits == 8 && (sft & 7) == 0;
-#define BAGS_PASS(IOTA, LB, BYTE)                                                                                  \
+        // the shared-memory attribute is per device and per kernel: set once for each
+#define BAGS_PASS(IOTA, LB, BYTE, ITEMS, HWM)                                                                      \
     do {                                                                                                           \
         static bool attr_set[64] = {};   /* per kernel variant (expansion site) and device */                      \
         if (!attr_set[cur_dev & 63]) {                                                                             \
-            BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB, BYTE>,                                \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_BYTES)); \
+            BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB, BYTE, ITEMS, HWM>,                    \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
+                                              (int)sort_smem_bytes(ITEMS)));                                       \
             attr_set[cur_dev & 63] = true;                                                                         \
         }                                                                                                          \
-        onesweep_pass_kernel<IOTA, LB, BYTE><<<ntiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(                       \
+        onesweep_pass_kernel<IOTA, LB, BYTE, ITEMS, HWM><<<ntiles, SORT_THREADS, sort_smem_bytes(ITEMS), st>>>(    \
             ki, vi, ko, vo, n, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status);                      \
+    } while (0)
+#define BAGS_PASS_I(IOTA, LB, BYTE)                                                                                \
+    do {                                                                                                           \
+        if (small && g_sort_hwmatch) BAGS_PASS(IOTA, LB, BYTE, SORT_ITEMS_SMALL, true);                            \
+        else if (small) BAGS_PASS(IOTA, LB, BYTE, SORT_ITEMS_SMALL, false);                                        \
+        else BAGS_PASS(IOTA, LB, BYTE, SORT_ITEMS, false);                                                         \
     } while (0)
 #define BAGS_PASS_LB(LB)                                                                                           \
     do {                                                                                                           \
-        if (iota && byte_digit) BAGS_PASS(true, LB, true);                                                         \
-        else if (iota) BAGS_PASS(true, LB, false);                                                                 \
-        else if (byte_digit) BAGS_PASS(false, LB, true);                                                           \
-        else BAGS_PASS(false, LB, false);                                                                          \
+        if (iota && byte_digit) BAGS_PASS_I(true, LB, true);                                                       \
+        else if (iota) BAGS_PASS_I(true, LB, false);                                                               \
+        else if (byte_digit) BAGS_PASS_I(false, LB, true);                                                         \
+        else BAGS_PASS_I(false, LB, false);                                                                        \
     } while (0)
-        if (g_sort_lookback == 4) BAGS_PASS_LB(4);
-        else if (g_sort_lookback == 16) BAGS_PASS_LB(16);
-        else if (g_sort_lookback == 32) BAGS_PASS_LB(32);
-        else BAGS_PASS_LB(8);
+        if (g_sort_lookback == 8) BAGS_PASS_LB(8);
+        else BAGS_PASS_LB(4);
 #undef BAGS_PASS_LB
+#undef BAGS_PASS_I
 #undef BAGS_PASS
         BAGS_LAUNCH_OK("onesweep_pass_kernel");
         u32* t;
@@ -575,9 +591,19 @@ int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cuda
     return 0;
 }
 
+int set_sort_small_tiles(int value) {
+    const int prev = g_sort_small_tiles;
+    if (value == 0 || value == 1) g_sort_small_tiles = value;
+    return prev;
+}
+int set_sort_hwmatch(int value) {
+    const int prev = g_sort_hwmatch;
+    if (value == 0 || value == 1) g_sort_hwmatch = value;
+    return prev;
+}
 int set_sort_lookback(int value) {
     const int prev = g_sort_lookback;
-    if (value == 4 || value == 8 || value == 16 || value == 32) g_sort_lookback = value;
+    if (value == 4 || value == 8) g_sort_lookback = value;
     return prev;
 }
 

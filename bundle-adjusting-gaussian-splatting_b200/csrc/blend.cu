@@ -536,6 +536,8 @@ extern "C" int bags_set_tuning(int knob, int value) {
         return prev;
     }
     if (knob == BAGS_TUNE_SORT_LOOKBACK) return bags::set_sort_lookback(value);
+    if (knob == BAGS_TUNE_SORT_SMALL_TILES) return bags::set_sort_small_tiles(value);
+    if (knob == BAGS_TUNE_SORT_HWMATCH) return bags::set_sort_hwmatch(value);
     int* target = knob == BAGS_TUNE_BLEND_FWD_PPT ? &bags::g_fwd_ppt : knob == BAGS_TUNE_BLEND_BWD_PPT ? &bags::g_bwd_ppt : nullptr;
     if (!target) return BAGS_E_INVALID;
     const int prev = *target;

@@ -57,8 +57,10 @@ inline void carve(char*& p, T*& out, size_t count) {
 
 // Radix-sort bookkeeping shared by the depth sort (P items) and the tile sort (R items).
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
+constexpr int SORT_ITEMS = 16;                         // keys per thread of a throughput-bound pass (several waves)
+constexpr int SORT_ITEMS_SMALL = 8;                   // ... of a latency-bound one (all CTAs resident at once)
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
+constexpr int SORT_TILE_SMALL = SORT_THREADS * SORT_ITEMS_SMALL;   // 2048; the scratch is sized for this one
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
@@ -71,7 +73,7 @@ struct SortScratch {
     size_t zero_bytes; // bytes from ghist to the end that must be zeroed before a sort
     int ntiles;
     static size_t bytes(int n) {
-        size_t nt = (size_t)(n + SORT_TILE - 1) / SORT_TILE;
+        size_t nt = (size_t)(n + SORT_TILE_SMALL - 1) / SORT_TILE_SMALL;
         if (nt == 0) nt = 1;
         return align_up(SORT_MAX_PASSES * RADIX * sizeof(u32)) + align_up(SORT_MAX_PASSES * sizeof(u32)) +
                align_up((size_t)SORT_MAX_PASSES * nt * RADIX * sizeof(u32));
@@ -79,9 +81,9 @@ struct SortScratch {
     static SortScratch from(char*& p, int n) {
         SortScratch s;
         char* p0 = p;
-        size_t nt = (size_t)(n + SORT_TILE - 1) / SORT_TILE;
+        size_t nt = (size_t)(n + SORT_TILE_SMALL - 1) / SORT_TILE_SMALL;
         if (nt == 0) nt = 1;
-        s.ntiles = (int)nt;
+        s.ntiles = (int)nt;      // capacity in tiles (stride of a pass's status words)
         carve(p, s.ghist, SORT_MAX_PASSES * RADIX);
         carve(p, s.tile_counter, SORT_MAX_PASSES);
         carve(p, s.status, (size_t)SORT_MAX_PASSES * nt * RADIX);
@@ -170,6 +172,8 @@ int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offs
 int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, const u32* offsets, BinningState& b,
                      int grid_x, cudaStream_t st);
 int set_sort_lookback(int value);
+int set_sort_small_tiles(int value);
+int set_sort_hwmatch(int value);
 int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st);
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);

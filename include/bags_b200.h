@@ -281,10 +281,12 @@ int bags_profile_read(double* ms, unsigned long long* calls);
  * summation order of the gradients.  BLEND_CULL: 1 (default) skips, per 8x4 patch, the splats whose alpha >= 1/255
  * bounding box misses the patch; 0 evaluates every splat of the tile list for every patch (must give the same forward
  * bits -- used by the tests).  SORT_LOOKBACK: predecessor status words the onesweep passes fetch per look-back
- * round (4, 8, 16 or 32; default 8; no effect on results).  Returns the previous value (other values only
+ * round (4 or 8; default 4; no effect on results).  SORT_SMALL_TILES: 1 (default) sorts 2048 instead of 4096 keys
+ * per CTA when a pass would not fill the GPU twice (latency-bound sizes, e.g. the 1 M-key depth sort); SORT_HWMATCH: 1
+ * ranks those small tiles with match.any instead of one vote per digit bit (default 0).  Returns the previous value (other values only
  * query), BAGS_E_INVALID for an unknown knob. */
 enum { BAGS_TUNE_BLEND_FWD_PPT = 0, BAGS_TUNE_BLEND_BWD_PPT = 1, BAGS_TUNE_BLEND_CULL = 2,
-       BAGS_TUNE_SORT_LOOKBACK = 3 };
+       BAGS_TUNE_SORT_LOOKBACK = 3, BAGS_TUNE_SORT_SMALL_TILES = 4, BAGS_TUNE_SORT_HWMATCH = 5 };
 int bags_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -212,10 +212,20 @@ def test_against_float64_oracle():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def test_onesweep_sort_matches_stable_sort():
+@pytest.mark.parametrize("small_tiles,hwmatch", [(1, 0), (0, 0), (1, 1)])
+def test_onesweep_sort_matches_stable_sort(small_tiles, hwmatch):
     import bags_capi as capi
     L = capi.lib()
     d = dev()
+    prev = (L.bags_set_tuning(4, small_tiles), L.bags_set_tuning(5, hwmatch))
+    try:
+        _check_sorts(L, d)
+    finally:
+        L.bags_set_tuning(4, prev[0])
+        L.bags_set_tuning(5, prev[1])
+
+
+def _check_sorts(L, d):
     for n, (b0, b1) in [(0, (0, 32)), (1, (0, 32)), (777, (0, 32)), (8192, (0, 13)), (8193, (0, 32)),
                         (300001, (0, 32)), (1_000_000, (3, 17)), (3_000_000, (0, 15)), (50_000, (5, 8)),
                         (12288, (8, 32)), (100_001, (0, 1)), (70_000, (2, 13)), (4097, (16, 22)),
