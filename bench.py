@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the views of a step are pipelined over (bags_view_parallel.ViewStreams): view "
                          "k's preprocess/binning/forward overlaps view k-1's backward; 1 = everything on one stream")
+    ap.add_argument("--step-sync", action="store_true",
+                    help="development: host-synchronize at the end of every device-leg step")
     ap.add_argument("--fused-loss", action="store_true",
                     help="e2e leg: bags_loss.l1_loss (fused kernels) instead of the torch operator sequence of "
                          "utils/loss_utils.py:18-19 that both arms run by default")
@@ -228,6 +230,8 @@ def main():
     use_dist = world > 1 and args.impl == "ours"
     if use_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout, next to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     mod = load_impl(args.impl)
@@ -294,6 +298,8 @@ def main():
         pipe.end()
         if use_dist:
             VP.allreduce_gradients(params)
+        if args.step_sync:
+            torch.cuda.current_stream().synchronize()
 
     copy_stream = torch.cuda.Stream(device=dev)
     if args.impl == "ours" and args.fused_loss:

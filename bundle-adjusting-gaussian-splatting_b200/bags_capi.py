@@ -60,6 +60,7 @@ SIGNATURES = {
     "bags_center_crop_backward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "bags_loss_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bags_loss_window": (c_int, [c_void_p]),
+    "bags_adam_step": (c_int, [c_int, c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, _P]),
     "bags_loss_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_unpack_state": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P,
@@ -71,6 +72,12 @@ SIGNATURES = {
     "bags_sort_scratch_bytes": (c_size_t, [c_int]),
     "bags_sort_pairs_u32": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
 }
+
+
+class AdamTensor(ctypes.Structure):
+    """struct bags_adam_tensor of include/bags_b200.h"""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("n", ctypes.c_longlong), ("step_size", ctypes.c_double), ("bias_correction2_sqrt", ctypes.c_double)]
 
 
 STAGES = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges", "blend_fwd", "bwd_clear", "blend_bwd",

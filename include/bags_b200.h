@@ -244,6 +244,24 @@ int bags_loss_forward(const float* img1, const float* img2, int planes, int H, i
 int bags_loss_backward(const float* img1, const float* img2, int planes, int H, int W, const float* d_mu1,
                        const float* d_e11, const float* d_e12, const float* coef, float* dL_dimg1, void* stream);
 
+/* Fused multi-tensor Adam step.  Replaces `torch.optim.Adam.step()` as the reference
+ * calls it (scene/gaussian_model.py:197-206 creates `torch.optim.Adam(l, lr=0.0, eps=1e-15)` over six parameter
+ * groups; train.py:420 steps it once per iteration): no weight decay, no amsgrad, not maximize.  One launch per 8
+ * tensors reads param / grad / exp_avg / exp_avg_sq once and writes param / exp_avg / exp_avg_sq once.
+ * `tensors` is a HOST array; the pointers inside are device pointers to contiguous fp32 arrays of n elements.
+ * step_size = -lr / (1 - beta1^t) and bias_correction2_sqrt = sqrt(1 - beta2^t) are computed by the caller in double
+ * for the tensor's own step count t (already incremented), exactly like torch's Python code. */
+typedef struct bags_adam_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    long long n;
+    double step_size;
+    double bias_correction2_sqrt;
+} bags_adam_tensor;
+int bags_adam_step(int ntensors, const bags_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream);
+
 /* Test-only view of the private state.  Any output pointer may be NULL.  All outputs are device pointers:
  *   tiles_touched [P] u32, depth_bits [P] u32 (float bits of the view-space depth, undefined for culled),
  *   xy [P,2] f32, conic_opacity [P,4] f32, rgb [P,3] f32,
