@@ -54,8 +54,9 @@ def parse():
     ap.add_argument("--step-sync", action="store_true",
                     help="development: host-synchronize at the end of every device-leg step")
     ap.add_argument("--fused-loss", action="store_true",
-                    help="e2e leg: bags_loss.l1_loss (fused kernels) instead of the torch operator sequence of "
-                         "utils/loss_utils.py:18-19 that both arms run by default")
+                    help="e2e leg: bags_loss.l1_loss_u8 (loss + gradient against the 8-bit ground truth in one "
+                         "kernel) instead of the torch operator sequence of utils/loss_utils.py:18-19 that both "
+                         "arms run by default")
     ap.add_argument("--trace", default="", help="development: write a GPU timeline summary of 2 device-leg and 2 "
                                                 "e2e steps (torch.profiler) to this JSON file; not a bench value")
     return ap.parse_args()
@@ -302,9 +303,11 @@ def main():
             torch.cuda.current_stream().synchronize()
 
     copy_stream = torch.cuda.Stream(device=dev)
+    l1_loss_u8 = None
     if args.impl == "ours" and args.fused_loss:
-        import bags_loss          # drop-in for utils/loss_utils.py:l1_loss (fused forward/backward kernels)
-        l1_loss = bags_loss.l1_loss
+        import bags_loss          # l1_loss against the 8-bit ground truth as stored: loss + gradient in one kernel
+        l1_loss_u8 = bags_loss.l1_loss_u8
+        l1_loss = None
     else:
         def l1_loss(network_output, gt):   # utils/loss_utils.py:18-19, the operator sequence the reference runs
             return torch.abs(network_output - gt).mean()
@@ -334,7 +337,10 @@ def main():
                 cur = torch.cuda.current_stream()
                 color, radii, depth, weights, _ = render(vw)
                 cur.wait_event(ev)
-                loss = l1_loss(color, vw["gt_dev"].float().mul_(1.0 / 255.0))
+                if l1_loss_u8 is not None:
+                    loss = l1_loss_u8(color, vw["gt_dev"])
+                else:
+                    loss = l1_loss(color, vw["gt_dev"].float().mul_(1.0 / 255.0))
                 pipe.before_backward()
                 loss.backward()
                 pipe.after_backward()

@@ -60,6 +60,8 @@ SIGNATURES = {
     "bags_center_crop_backward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "bags_loss_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bags_loss_window": (c_int, [c_void_p]),
+    "bags_l1_u8_scratch_bytes": (c_size_t, [ctypes.c_longlong]),
+    "bags_l1_u8_forward": (c_int, [_P, _P, ctypes.c_longlong, _P, _P, _P, _P]),
     "bags_adam_step": (c_int, [c_int, c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, _P]),
     "bags_loss_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),

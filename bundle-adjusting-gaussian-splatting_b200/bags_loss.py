@@ -101,3 +101,42 @@ def training_loss(image, gt_image, lambda_dssim=0.2):
     """train.py:325: (1 - lambda) * Ll1 + lambda * (1 - ssim).  Returns (loss, Ll1, ssim)."""
     Ll1, s = l1_ssim(image, gt_image)
     return (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - s), Ll1, s
+
+
+class _L1U8(torch.autograd.Function):
+    """(render fp32, ground truth uint8) -> mean |render - gt / 255| with its gradient formed in the same pass."""
+
+    @staticmethod
+    def forward(ctx, img, gt_u8):
+        if not (img.is_cuda and gt_u8.is_cuda):
+            raise RuntimeError("bags_b200: the fused loss needs CUDA tensors (there is no CPU path)")
+        if gt_u8.dtype != torch.uint8 or img.shape != gt_u8.shape:
+            raise RuntimeError("l1_loss_u8: expected a uint8 ground truth of the render's shape")
+        dev = img.device
+        a = img.detach().to(torch.float32).contiguous()
+        b = gt_u8.contiguous()
+        n = a.numel()
+        L = capi.lib()
+        grad = torch.empty_like(a)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        scratch = torch.empty((int(L.bags_l1_u8_scratch_bytes(n)),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            rc = L.bags_l1_u8_forward(_ptr(a), _ptr(b), n, _ptr(grad), _ptr(loss), _ptr(scratch), stream)
+        capi.check(rc, "bags_l1_u8_forward")
+        ctx.save_for_backward(grad)
+        ctx.meta = (img.shape, img.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        shape, dtype = ctx.meta
+        return (grad * g).view(shape).to(dtype), None
+
+
+def l1_loss_u8(network_output, gt_u8):
+    """l1_loss (utils/loss_utils.py:18-19) against the ground truth as the data set stores it: uint8, scaled by
+    1/255 inside the kernel (what utils/general_utils.py:PILtoTorch does once at load time).  One kernel produces the
+    loss and its gradient; the ground truth stays 8-bit in HBM (4x less memory and H2D traffic per view)."""
+    return _L1U8.apply(network_output, gt_u8)

@@ -538,6 +538,7 @@ extern "C" int bags_set_tuning(int knob, int value) {
     if (knob == BAGS_TUNE_SORT_LOOKBACK) return bags::set_sort_lookback(value);
     if (knob == BAGS_TUNE_SORT_SMALL_TILES) return bags::set_sort_small_tiles(value);
     if (knob == BAGS_TUNE_SORT_HWMATCH) return bags::set_sort_hwmatch(value);
+    if (knob == BAGS_TUNE_PBWD_MIN_BLOCKS) return bags::set_pbwd_min_blocks(value);
     int* target = knob == BAGS_TUNE_BLEND_FWD_PPT ? &bags::g_fwd_ppt : knob == BAGS_TUNE_BLEND_BWD_PPT ? &bags::g_bwd_ppt : nullptr;
     if (!target) return BAGS_E_INVALID;
     const int prev = *target;

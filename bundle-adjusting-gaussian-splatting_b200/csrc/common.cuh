@@ -174,6 +174,7 @@ int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, co
 int set_sort_lookback(int value);
 int set_sort_small_tiles(int value);
 int set_sort_hwmatch(int value);
+int set_pbwd_min_blocks(int value);
 int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st);
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);

@@ -304,3 +304,97 @@ extern "C" int bags_loss_backward(const float* img1, const float* img2, int plan
     BAGS_LAUNCH_OK("loss_bwd_kernel");
     return 0;
 }
+
+// =================================================================================================================
+// L1 against an 8-bit ground truth, forward and gradient in one pass.
+//
+// The data set stores 8-bit images; the reference converts them to fp32 once (utils/general_utils.py PILtoTorch:
+// `/ 255.0`) and evaluates l1_loss = mean |render - gt| (utils/loss_utils.py:18-19) with autograd's mirror
+// (sign(render - gt) / numel) behind it: about ten element-wise passes over the image per iteration.  Here one kernel
+// reads the render (fp32) and the ground truth as stored (uint8, scaled by 1/255 in registers like PILtoTorch's
+// division), writes d(mean |.|)/d(render) = sign / numel and a per-CTA partial sum; a second tiny kernel adds the
+// partials in a fixed order in double and writes the fp32 mean.  Deterministic.
+// =================================================================================================================
+namespace bags {
+
+constexpr int L1U8_THREADS = 256;
+constexpr int L1U8_ITEMS = 16;     // elements per thread: four 16-byte fp32 loads + one 16-byte u8 load
+
+__global__ void __launch_bounds__(L1U8_THREADS)
+l1_u8_fwd_kernel(const float* __restrict__ img, const uint8_t* __restrict__ gt, long long n, float inv_n,
+                 float* __restrict__ dL_dimg, float* __restrict__ partial, int vec) {
+    __shared__ float s_red[8];
+    const long long base = ((long long)blockIdx.x * L1U8_THREADS + threadIdx.x) * L1U8_ITEMS;
+    float acc = 0.f;
+    if (vec && base + L1U8_ITEMS <= n) {
+        const uint4 g16 = *reinterpret_cast<const uint4*>(gt + base);
+        const unsigned int gw[4] = {g16.x, g16.y, g16.z, g16.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 x = *reinterpret_cast<const float4*>(img + base + 4 * q);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            float gs[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float y = (float)((gw[q] >> (8 * k)) & 0xffu) / 255.0f;
+                const float d = xs[k] - y;
+                acc += fabsf(d);
+                gs[k] = d > 0.f ? inv_n : (d < 0.f ? -inv_n : 0.f);
+            }
+            *reinterpret_cast<float4*>(dL_dimg + base + 4 * q) = make_float4(gs[0], gs[1], gs[2], gs[3]);
+        }
+    } else {
+        for (int k = 0; k < L1U8_ITEMS; k++) {
+            const long long i = base + k;
+            if (i >= n) break;
+            const float d = img[i] - (float)gt[i] / 255.0f;
+            acc += fabsf(d);
+            dL_dimg[i] = d > 0.f ? inv_n : (d < 0.f ? -inv_n : 0.f);
+        }
+    }
+    const float t = block_sum_256(acc, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(256)
+l1_u8_finalize_kernel(const float* __restrict__ partial, int nblocks, double inv_n, float* __restrict__ loss) {
+    __shared__ double s_a[256];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) a += (double)partial[i];
+    s_a[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_a[threadIdx.x] += s_a[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(s_a[0] * inv_n);
+}
+
+static inline long long l1_u8_blocks(long long n) {
+    const long long per = (long long)L1U8_THREADS * L1U8_ITEMS;
+    return (n + per - 1) / per;
+}
+
+}  // namespace bags
+
+extern "C" size_t bags_l1_u8_scratch_bytes(long long n) {
+    if (n < 0) return 0;
+    return align_up((size_t)l1_u8_blocks(n) * sizeof(float)) + 256;
+}
+
+extern "C" int bags_l1_u8_forward(const float* img, const uint8_t* gt, long long n, float* dL_dimg, float* loss,
+                                  char* scratch, void* stream) {
+    if (!img || !gt || !dL_dimg || !loss || !scratch || n < 1 || l1_u8_blocks(n) > 0x7fffffffll) {
+        set_error("bags_l1_u8_forward: invalid argument");
+        return BAGS_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = reinterpret_cast<float*>(align_up((size_t)scratch));
+    const int nb = (int)l1_u8_blocks(n);
+    const int vec = ((((size_t)img | (size_t)gt | (size_t)dL_dimg) & 15) == 0) ? 1 : 0;
+    l1_u8_fwd_kernel<<<nb, L1U8_THREADS, 0, st>>>(img, gt, n, (float)(1.0 / (double)n), dL_dimg, partial, vec);
+    BAGS_LAUNCH_OK("l1_u8_fwd_kernel");
+    l1_u8_finalize_kernel<<<1, 256, 0, st>>>(partial, nb, 1.0 / (double)n, loss);
+    BAGS_LAUNCH_OK("l1_u8_finalize_kernel");
+    return 0;
+}

@@ -178,8 +178,9 @@ __device__ __forceinline__ void load_cov3d(int idx, const float* cov3D_precomp, 
 
 // ACCUM = false: `acc_mask` is ignored (every dense row is written).  ACCUM = true: the outputs selected by acc_mask
 // are accumulated (separate instantiation, so the plain path keeps its register count).
-template <bool ACCUM>
-__global__ void __launch_bounds__(PB_THREADS, 5)
+// MINB: resident CTAs per SM the register allocation is held to (5 -> 96 registers, 6 -> 80 with 36 bytes of spills).
+template <bool ACCUM, int MINB>
+__global__ void __launch_bounds__(PB_THREADS, MINB)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
                       const float* __restrict__ shs, const float* __restrict__ scales,
                       const float* __restrict__ rotations, float scale_modifier,
@@ -603,6 +604,13 @@ __global__ void pose_finalize_kernel(int P, const float* __restrict__ means3D, c
     }
 }
 
+static int g_pbwd_minb = 5;
+int set_pbwd_min_blocks(int value) {
+    const int prev = g_pbwd_minb;
+    if (value == 5 || value == 6) g_pbwd_minb = value;
+    return prev;
+}
+
 int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, double* pose_acc, const BwdOut& o,
                           unsigned accumulate_mask, cudaStream_t st) {
     const int blocks = (a.P + PB_THREADS - 1) / PB_THREADS;
@@ -611,7 +619,9 @@ int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gac
         set_error("preprocess_bwd: %d SH coefficients per Gaussian do not fit the staging tile", a.M);
         return BAGS_E_INVALID;
     }
-    auto kern = accumulate_mask ? preprocess_bwd_kernel<true> : preprocess_bwd_kernel<false>;
+    auto kern = g_pbwd_minb == 6
+                    ? (accumulate_mask ? preprocess_bwd_kernel<true, 6> : preprocess_bwd_kernel<false, 6>)
+                    : (accumulate_mask ? preprocess_bwd_kernel<true, 5> : preprocess_bwd_kernel<false, 5>);
     if (smem > 48 * 1024)
         BAGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int vec4 = ((3 * a.M) % 4 == 0) && (((size_t)a.shs & 15) == 0) && (((size_t)o.dL_dsh & 15) == 0);

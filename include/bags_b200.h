@@ -244,6 +244,13 @@ int bags_loss_forward(const float* img1, const float* img2, int planes, int H, i
 int bags_loss_backward(const float* img1, const float* img2, int planes, int H, int W, const float* d_mu1,
                        const float* d_e11, const float* d_e12, const float* coef, float* dL_dimg1, void* stream);
 
+/* l1_loss against the ground truth as the data set stores it (uint8, scaled by 1/255 like PILtoTorch's division):
+ * loss[0] = mean |img - gt/255| (device fp32 scalar, fixed-order reduction) and dL_dimg = sign(img - gt/255) / n in
+ * one pass over n contiguous elements.  `scratch` must hold bags_l1_u8_scratch_bytes(n) bytes. */
+size_t bags_l1_u8_scratch_bytes(long long n);
+int bags_l1_u8_forward(const float* img, const uint8_t* gt, long long n, float* dL_dimg, float* loss, char* scratch,
+                       void* stream);
+
 /* Fused multi-tensor Adam step.  Replaces `torch.optim.Adam.step()` as the reference
  * calls it (scene/gaussian_model.py:197-206 creates `torch.optim.Adam(l, lr=0.0, eps=1e-15)` over six parameter
  * groups; train.py:420 steps it once per iteration): no weight decay, no amsgrad, not maximize.  One launch per 8
@@ -301,10 +308,12 @@ int bags_profile_read(double* ms, unsigned long long* calls);
  * bits -- used by the tests).  SORT_LOOKBACK: predecessor status words the onesweep passes fetch per look-back
  * round (4 or 8; default 4; no effect on results).  SORT_SMALL_TILES: 1 (default) sorts 2048 instead of 4096 keys
  * per CTA when a pass would not fill the GPU twice (latency-bound sizes, e.g. the 1 M-key depth sort); SORT_HWMATCH: 1
- * ranks those small tiles with match.any instead of one vote per digit bit (default 0).  Returns the previous value (other values only
+ * ranks those small tiles with match.any instead of one vote per digit bit (default 0).  PBWD_MIN_BLOCKS: resident CTAs
+ * per SM the backward preprocess kernel is compiled for (5 = 96 registers, default; 6 = 80 registers).  Returns the previous value (other values only
  * query), BAGS_E_INVALID for an unknown knob. */
 enum { BAGS_TUNE_BLEND_FWD_PPT = 0, BAGS_TUNE_BLEND_BWD_PPT = 1, BAGS_TUNE_BLEND_CULL = 2,
-       BAGS_TUNE_SORT_LOOKBACK = 3, BAGS_TUNE_SORT_SMALL_TILES = 4, BAGS_TUNE_SORT_HWMATCH = 5 };
+       BAGS_TUNE_SORT_LOOKBACK = 3, BAGS_TUNE_SORT_SMALL_TILES = 4, BAGS_TUNE_SORT_HWMATCH = 5,
+       BAGS_TUNE_PBWD_MIN_BLOCKS = 6 };
 int bags_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -1,0 +1,36 @@
+"""GPU parity of bags_loss.l1_loss_u8 (loss + gradient against the 8-bit ground truth in one kernel) with the
+reference's operator sequence: PILtoTorch's `/ 255.0` (utils/general_utils.py) then l1_loss (utils/loss_utils.py:18-19)
+and autograd."""
+import pytest
+import torch
+
+from oracle import post_oracle as PO
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(3, 1080, 1920), (3, 37, 53), (1, 5, 7), (3, 840, 1297)], ids=str)
+def test_l1_u8_matches_reference_sequence(shape):
+    import bags_loss as BL
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(sum(shape))
+    img = torch.rand(*shape, generator=g).to(dev)
+    gt = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).to(dev)
+    img[..., :2, :] = gt[..., :2, :].float() / 255.0                    # exact ties: gradient must be exactly 0 there
+    a = img.clone().requires_grad_(True)
+    loss = BL.l1_loss_u8(a, gt)
+    (loss * 3.0).backward()
+    b = img.clone().requires_grad_(True)
+    want = PO.l1_loss(b, gt.float() / 255.0)
+    (want * 3.0).backward()
+    w64 = PO.l1_loss(img.double(), gt.double() / 255.0)
+    assert abs(float(loss) - float(w64)) <= 1e-6
+    assert abs(float(loss) - float(want)) <= 2e-6
+    assert torch.equal(a.grad, b.grad)                                  # +-3/n or 0: exact
+    assert float(a.grad[..., :2, :].abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        BL.l1_loss_u8(img.cpu(), gt.cpu())
+    with pytest.raises(RuntimeError):
+        BL.l1_loss_u8(img, gt.float())

@@ -65,7 +65,7 @@ def main():
     ap.add_argument("--skip-ref", action="store_true")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
-    keep = ("metric", "value", "ms_per_step", "config", "stages", "preprocess_binning", "impl", "error", "clocks")
+    keep = ("metric", "value", "ms_per_step", "ms_per_step_regions", "config", "stages", "preprocess_binning", "impl", "error", "clocks")
     with open(a.out, "w") as f:
         def emit(tag, line):
             line = {k: v for k, v in line.items() if k in keep}
