@@ -8,9 +8,9 @@ Contract (see DESIGN.md "Measurement"): a step = one training iteration over `vi
 Gaussian-parameter gradients accumulate in one flat buffer and (N>1) are summed with one NCCL all-reduce.
 `value` = views/s with the upstream image gradients resident in HBM; `e2e` = the same through host buffers: each
 view's 8-bit ground-truth image comes from pinned host memory (H2D on a copy stream, prefetched one view ahead), is
-converted to fp32 on the device, the L1 loss (the torch operator sequence of utils/loss_utils.py:18-19 in both arms;
---fused-loss switches ours to bags_loss.l1_loss) is computed on the device and read back (D2H) inside the timed
-region.  Prints ONE JSON line on rank 0.
+and the L1 loss is computed on the device (ours: bags_loss.l1_loss_u8, loss + gradient against the 8-bit image in
+one kernel; reference arm and --torch-loss: uint8 -> fp32 / 255 and the torch operator sequence of
+utils/loss_utils.py:18-19) and read back (D2H) inside the timed region.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -53,10 +53,10 @@ def parse():
                          "k's preprocess/binning/forward overlaps view k-1's backward; 1 = everything on one stream")
     ap.add_argument("--step-sync", action="store_true",
                     help="development: host-synchronize at the end of every device-leg step")
-    ap.add_argument("--fused-loss", action="store_true",
-                    help="e2e leg: bags_loss.l1_loss_u8 (loss + gradient against the 8-bit ground truth in one "
-                         "kernel) instead of the torch operator sequence of utils/loss_utils.py:18-19 that both "
-                         "arms run by default")
+    ap.add_argument("--torch-loss", action="store_true",
+                    help="e2e leg of our arm: the torch operator sequence of utils/loss_utils.py:18-19 (what the "
+                         "reference arm always runs) instead of bags_loss.l1_loss_u8 (loss + gradient against the "
+                         "8-bit ground truth in one kernel)")
     ap.add_argument("--trace", default="", help="development: write a GPU timeline summary of 2 device-leg and 2 "
                                                 "e2e steps (torch.profiler) to this JSON file; not a bench value")
     return ap.parse_args()
@@ -304,7 +304,7 @@ def main():
 
     copy_stream = torch.cuda.Stream(device=dev)
     l1_loss_u8 = None
-    if args.impl == "ours" and args.fused_loss:
+    if args.impl == "ours" and not args.torch_loss:
         import bags_loss          # l1_loss against the 8-bit ground truth as stored: loss + gradient in one kernel
         l1_loss_u8 = bags_loss.l1_loss_u8
         l1_loss = None
