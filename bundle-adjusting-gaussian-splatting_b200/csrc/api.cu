@@ -423,7 +423,9 @@ extern "C" int bags_rasterize_backward_accum(
     if (P > 0) {
         BAGS_REQUIRE(background && means3D && viewmatrix && projmatrix && campos && radii, "null required input");
         BAGS_REQUIRE(geom_buffer && binning_buffer && image_buffer, "null state buffer");
-        BAGS_REQUIRE(dL_dpix && dL_dpix_depth && dL_dalpha, "null upstream gradient");
+        // dL_dpix_depth / dL_dalpha may be NULL = "no gradient reaches the depth / weight image" (all zeros): what
+        // autograd's undefined gradient means; the reference always receives materialised zero tensors
+        BAGS_REQUIRE(dL_dpix, "null upstream colour gradient");
         BAGS_REQUIRE(dL_dmean2D && dL_dmean2D_densify && covariance && dL_dopacity && dL_dcolor && dL_dmean3D &&
                          dL_dcov3D && dL_dscale && dL_drot,
                      "null dense output");

@@ -362,8 +362,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
             g.x = dL_dpixels[0 * plane + pix_id];
             g.y = dL_dpixels[1 * plane + pix_id];
             g.z = dL_dpixels[2 * plane + pix_id];
-            g.w = dL_dpixel_depths[pix_id];
-            w = dL_dalphas[pix_id];
+            g.w = dL_dpixel_depths ? dL_dpixel_depths[pix_id] : 0.f;   // NULL: no gradient w.r.t. the depth image
+            w = dL_dalphas ? dL_dalphas[pix_id] : 0.f;                  // NULL: none w.r.t. the weight image
         }
         float bg_dot_dpixel = 0;
         bg_dot_dpixel += bg0 * g.x;

@@ -19,7 +19,7 @@ def _ptr(t):
     optional inputs (mirrors data_ptr() of an empty tensor in the reference binding)."""
     if t is None or t.numel() == 0:
         return None
-    return ctypes.c_void_p(t.data_ptr())
+    return t.data_ptr()          # a plain int: ctypes converts it for the c_void_p parameters of bags_capi.SIGNATURES
 
 
 def _f32c(t, device):

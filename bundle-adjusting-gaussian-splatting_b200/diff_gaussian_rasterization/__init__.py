@@ -115,6 +115,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         num_rendered, color, depth, weights, radii, geomBuffer, binningBuffer, imgBuffer, means2Dx, means2Dy = out
 
         mean2D = torch.cat((means2Dx, means2Dy), dim=-1)
+        # undefined upstream gradients arrive as None instead of freshly zero-filled images (train.py's loss only
+        # touches the colour image): the backward passes NULL for them and the kernel reads zeros
+        ctx.set_materialize_grads(False)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.camera_center = camera_center
@@ -130,6 +133,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer,
          weights) = ctx.saved_tensors
+        if grad_out_color is None:
+            if grad_out_depth is None and grad_out_weight is None:
+                return (None,) * 15                   # nothing differentiable was used (mean2D / radii carry no gradient)
+            grad_out_color = torch.zeros((3, rs.image_height, rs.image_width), dtype=torch.float32,
+                                         device=means3D.device)
         args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 ctx.world_view, ctx.full_proj, rs.intrinsic, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width,
                 grad_out_color, grad_out_depth, grad_out_weight, sh, rs.sh_degree, ctx.camera_center, geomBuffer,

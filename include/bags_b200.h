@@ -96,7 +96,9 @@ int bags_rasterize_forward(
  *   (= accumulated conic trace + 1e-4, rasterize_points.cu:274).
  * Pose / intrinsic outputs, already reduced as mean over all P rows like the reference's .mean(0):
  *   dL_dcampos [3], dL_dprojmatrix [16], dL_dviewmatrix [16], dL_dshift [3].
- * `scratch` must hold bags_backward_scratch_bytes(P) bytes (contents undefined on entry). */
+ * `scratch` must hold bags_backward_scratch_bytes(P) bytes (contents undefined on entry).
+ * dL_dpix_depth and / or dL_dalpha may be NULL: no gradient reaches the depth / weight image (treated as zeros; the
+ * reference always receives materialised zero tensors from autograd). */
 int bags_rasterize_backward(
     int P, int D, int M, int R,
     const float* background,

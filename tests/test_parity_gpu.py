@@ -549,3 +549,51 @@ def test_view_streams_pipeline_equals_serial(sinks):
         assert torch.equal(a, b)                      # the forward is deterministic
     for a, b in zip(pose2, pose1):
         assert pc.rel_l2(a, b) <= 1e-5
+
+
+def test_undefined_depth_and_weight_gradients_equal_zero_gradients():
+    """A loss that only touches the colour image (train.py's): autograd hands None for the depth / weight gradients,
+    the wrapper passes NULL and the kernel reads zeros -- same gradients as explicit zero images (what the reference
+    receives), up to the run-to-run atomic-order noise."""
+    mod = pc.load_ours()
+    d = dev()
+    W, H, P = 200, 136, 8000
+    cam = S.make_camera(W, H, seed=100)
+    gs = S.make_gaussians(P, cam, seed=0, scale=0.03)
+    up_c = S.make_upstream(H, W, seed=1)[0].to(d)
+
+    def run(explicit_zeros):
+        leaves = {k: getattr(gs, k).to(d).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales",
+                                                                          "rotations")}
+        view = cam.viewmatrix.to(d).requires_grad_(True)
+        proj = cam.projmatrix.to(d).requires_grad_(True)
+        campos = cam.campos.to(d).requires_grad_(True)
+        shift = torch.zeros(3, device=d, requires_grad=True)
+        st = mod.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.ones(3, device=d),
+            scale_modifier=1.0, viewmatrix=view, projmatrix=proj, intrinsic=cam.intrinsic.to(d), sh_degree=3,
+            campos=campos, prefiltered=False, debug=False, debug_iter=0)
+        m2d = torch.zeros(P, 3, device=d, requires_grad=True)
+        m2dd = torch.zeros(P, 3, device=d, requires_grad=True)
+        color, radii, depth, weights, _ = mod.GaussianRasterizer(raster_settings=st)(
+            means3D=leaves["means3D"], means2D=m2d, means2D_densify=m2dd, shift_factors=shift,
+            opacities=leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+        if explicit_zeros:
+            torch.autograd.backward([color, depth, weights], [up_c, torch.zeros_like(depth), torch.zeros_like(weights)])
+        else:
+            torch.autograd.backward([color], [up_c])
+        return [leaves[k].grad for k in leaves] + [m2d.grad, m2dd.grad, view.grad, proj.grad, campos.grad]
+
+    a, b = run(False), run(True)
+    for x, y in zip(a, b):
+        assert x is not None and pc.rel_l2(x, y) <= 1e-5
+    # and a graph in which nothing differentiable is used must not fail
+    leaves = gs.means3D.to(d).requires_grad_(True)
+    st = mod.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, torch.zeros(3, device=d), 1.0,
+                                           cam.viewmatrix.to(d), cam.projmatrix.to(d), cam.intrinsic.to(d), 3,
+                                           cam.campos.to(d), False, False, 0)
+    out = mod.GaussianRasterizer(st)(leaves, torch.zeros(P, 3, device=d), torch.zeros(P, 3, device=d),
+                                     torch.zeros(3, device=d), gs.opacities.to(d), shs=gs.shs.to(d),
+                                     scales=gs.scales.to(d), rotations=gs.rotations.to(d))
+    (out[4].sum() * 0.0 + leaves.sum()).backward()
+    assert leaves.grad is not None
