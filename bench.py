@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=2,
                     help="CUDA streams the views of a step are pipelined over (bags_view_parallel.ViewStreams): view "
                          "k's preprocess/binning/forward overlaps view k-1's backward; 1 = everything on one stream")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: keep the round-robin view assignment instead of balancing it by tile instances")
     ap.add_argument("--step-sync", action="store_true",
                     help="development: host-synchronize at the end of every device-leg step")
     ap.add_argument("--torch-loss", action="store_true",
@@ -259,17 +261,18 @@ def main():
         params.enable_direct_accumulation(mod)
     bg = torch.zeros(3, device=dev)
     shift = torch.zeros(3, device=dev, requires_grad=True)
-    views = []
-    for v in my_views:
+    def make_view(v):
         cam = S.make_camera(W, H, seed=100 + v)
         g = torch.Generator().manual_seed(1000 + v)
         # ground truth as the dataset stores it: 8-bit RGB in pinned host memory, converted to fp32 on the device
         gt_host = torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8).pin_memory()
         up = [u.to(dev) for u in S.make_upstream(H, W, seed=1 + v)]
-        views.append(dict(
-            view=cam.viewmatrix.to(dev).requires_grad_(True), proj=cam.projmatrix.to(dev).requires_grad_(True),
+        return dict(
+            id=v, view=cam.viewmatrix.to(dev).requires_grad_(True), proj=cam.projmatrix.to(dev).requires_grad_(True),
             campos=cam.campos.to(dev).requires_grad_(True), intrinsic=cam.intrinsic.to(dev), cam=cam,
-            gt_host=gt_host, gt_dev=torch.empty(3, H, W, device=dev, dtype=torch.uint8), up=up))
+            gt_host=gt_host, gt_dev=torch.empty(3, H, W, device=dev, dtype=torch.uint8), up=up)
+
+    views = [make_view(v) for v in my_views]
 
     def render(vw):
         st = mod.GaussianRasterizationSettings(
@@ -282,6 +285,34 @@ def main():
         return rast(means3D=params["means3D"], means2D=m2d, means2D_densify=m2dd, shift_factors=shift,
                     opacities=params["opacities"], shs=params["shs"], scales=params["scales"],
                     rotations=params["rotations"])
+
+    # ---- view -> rank assignment balanced by measured work (N > 1) -----------------------------------------------
+    # The step time of view-parallel training is the time of the slowest rank, and the tile-instance count of the
+    # bench cameras differs by up to 3x.  Every rank renders its round-robin views once, the counts are all-gathered
+    # and bags_view_parallel.balance_views deals the same 4N views out again, the same number per rank.
+    assignment = "round-robin (rank r: views r, r+N, ...)"
+    if use_dist and not args.no_balance:
+        counts = []
+        for vw in views:
+            c = render(vw)[0]
+            counts.append(int(c.grad_fn.num_rendered))
+            del c
+        mine = torch.tensor(counts, dtype=torch.int64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        cost = [0] * nviews
+        for r in range(world):
+            for k, v in enumerate(range(r, nviews, world)):
+                cost[v] = int(every[r][k])
+        table = VP.balance_views(cost, world)
+        loads = [sum(cost[v] for v in q) for q in table]
+        rr = [sum(cost[v] for v in range(r, nviews, world)) for r in range(world)]
+        assignment = (f"balanced by tile instances (bags_view_parallel.balance_views): max/mean work "
+                      f"{max(loads) / (sum(loads) / world):.3f} (round-robin: {max(rr) / (sum(rr) / world):.3f})")
+        if table[rank] != my_views:
+            my_views = table[rank]
+            views = [make_view(v) for v in my_views]
+        torch.cuda.empty_cache()
 
     pipe = VP.ViewStreams(dev, depth=args.streams if args.impl == "ours" else 1)
     pipe_serial = VP.ViewStreams(dev, depth=1)
@@ -484,7 +515,7 @@ def main():
                                f"(fwd+bwd incl. pose/intrinsic grads), median scale {SCALE}",
                    "views_per_step": nviews, "visible_mean": V, "tile_instances_mean": R, "l2": "per-view working set (236 B x P inputs + state) "
                    "exceeds the 126 MB L2; no explicit flush", "parallelism": f"view-dp{world}",
-                   "streams": pipe.depth,
+                   "view_assignment": assignment, "streams": pipe.depth,
                    "grad_accumulation": "kernel adds into the flat gradient buffer (register_grad_sink)" if grad_sinks
                    else "autograd (fresh gradient tensors + add)"},
         "clocks": clocks,
