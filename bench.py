@@ -233,8 +233,9 @@ def main():
     use_dist = world > 1 and args.impl == "ours"
     if use_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout, next to the one JSON line
+        # NCCL writes its debug output (the image sets NCCL_DEBUG=VERSION: a version banner) to stdout, next to the
+        # one JSON line; send it to stderr whatever level the caller chose
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     mod = load_impl(args.impl)
