@@ -218,15 +218,40 @@ def trace_steps(fns, path):
     json.dump(out, open(path, "w"), indent=1)
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on
+    stdout when the image sets NCCL_DEBUG=VERSION, whatever NCCL_DEBUG_FILE says): keep a private duplicate of the
+    real stdout for the JSON line and point file descriptor 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    guard_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference" and rank != 0:
         return 0
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: bench.py measures the CUDA path and has no CPU fallback"}))
+        emit({"error": "no CUDA device: bench.py measures the CUDA path and has no CPU fallback"})
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -240,8 +265,8 @@ def main():
 
     mod = load_impl(args.impl)
     if mod is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run oracle/build_ref.py where "
-                                                             "/root/reference exists)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built (run oracle/build_ref.py where "
+                                                  "/root/reference exists)"})
         return 0
 
     cfg = S.CONFIGS[args.config]
@@ -530,7 +555,7 @@ def main():
         line["e2e"] = {"value": e2e["value"] if e2e else value, "unit": "views/s",
                        "h2d_bytes_per_step": e2e["h2d_bytes_per_step"] if e2e else 0,
                        "d2h_bytes_per_step": e2e["d2h_bytes_per_step"] if e2e else 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     line["e2e"] = e2e
@@ -578,7 +603,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline_sample()
         except Exception as ex:  # the baseline is a report, not the product
             line["cpu_baseline"] = {"error": repr(ex)}
-    print(json.dumps(line))
+    emit(line)
     if use_dist:
         dist.destroy_process_group()
     return 0
