@@ -494,7 +494,8 @@ def main():
         launches0 = capi.lib().bags_launch_count()
     ms, ms_all = timed(step_device, args.steps)
     if capi is not None:
-        launches = int(capi.lib().bags_launch_count() - launches0)
+        # launches of one timed region (all regions run the same steps)
+        launches = int(capi.lib().bags_launch_count() - launches0) // max(1, args.repeats)
 
     e2e = None
     if not args.no_e2e:
