@@ -141,16 +141,34 @@ def allreduce_gradients(params: FlatGaussianParams, group=None, async_op: bool =
     return dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+def gather_view_costs(local_costs: Sequence[float], num_views: int, rank: int, world: int, group=None) -> List[float]:
+    """Per-view work estimates of ALL views from the ones every rank measured for its round-robin share
+    (`shard_views`): one all_gather_object of a few numbers.  Without a process group the local list is the result."""
+    mine = [float(c) for c in local_costs]
+    if not (dist.is_available() and dist.is_initialized()) or world == 1:
+        return mine
+    every = [None] * world
+    dist.all_gather_object(every, mine, group=group)
+    costs = [0.0] * num_views
+    for r in range(world):
+        for k, v in enumerate(shard_views(num_views, r, world)):
+            costs[v] = every[r][k]
+    return costs
+
+
 def run_views(params: FlatGaussianParams, views: Sequence, view_loss: Callable, num_views_total: int = None,
-              rank: int = 0, world: int = 1, group=None):
+              rank: int = 0, world: int = 1, group=None, assignment: Sequence[Sequence[int]] = None):
     """Gradient accumulation over this rank's share of `views`, then one all-reduce.
 
     `view_loss(params, view) -> scalar loss tensor` renders one view and returns its loss; per-view pose gradients
-    land on that view's own leaves.  Returns the list of local losses (python floats are NOT taken: no host sync).
+    land on that view's own leaves.  `assignment` (e.g. from `balance_views`) overrides the round-robin share:
+    `assignment[rank]` lists this rank's views.  Returns the list of local losses (python floats are NOT taken: no
+    host sync).
     """
     n = len(views) if num_views_total is None else num_views_total
     losses = []
-    for vi in shard_views(n, rank, world):
+    mine = shard_views(n, rank, world) if assignment is None else list(assignment[rank])
+    for vi in mine:
         loss = view_loss(params, views[vi])
         loss.backward()
         losses.append(loss.detach())

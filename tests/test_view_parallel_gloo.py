@@ -85,6 +85,23 @@ def _worker(rank, world, port, out_dir):
     views = _make_views(NV, W, H)
     VP.run_views(fp, views, _oracle_view_loss, rank=rank, world=world)
     torch.save(fp.flat_grad.clone(), os.path.join(out_dir, f"grad_{rank}.pt"))
+    # second iteration with the view -> rank table balanced by measured work (tile instances of each rank's own views,
+    # exchanged with one all_gather_object): the reduced gradients do not depend on who rendered what
+    sys.path.insert(0, ROOT)
+    from oracle import raster_oracle as O
+    local = []
+    for vi in VP.shard_views(NV, rank, world):
+        cam = views[vi][0]
+        sc = O.Scene(gs.means3D, gs.opacities, cam.viewmatrix, cam.projmatrix, cam.campos, cam.W, cam.H, cam.tanfovx,
+                     cam.tanfovy, (0, 0, 0), shs=gs.shs, scales=gs.scales, rotations=gs.rotations,
+                     shift_factors=torch.zeros(3), sh_degree=3)
+        local.append(O.rasterize_forward(sc)["num_rendered"])
+    costs = VP.gather_view_costs(local, NV, rank, world)
+    table = VP.balance_views(costs, world)
+    fp.zero_grad()
+    VP.run_views(fp, views, _oracle_view_loss, rank=rank, world=world, assignment=table)
+    torch.save({"grad": fp.flat_grad.clone(), "table": table, "costs": costs},
+               os.path.join(out_dir, f"balanced_{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -104,4 +121,12 @@ def test_two_ranks_equal_sum_of_single_view_gradients(tmp_path):
     VP.run_views(fp, _make_views(NV, W, H), _oracle_view_loss, rank=0, world=1)
     assert float(fp.flat_grad.abs().max()) > 0
     rel = float((g0 - fp.flat_grad).norm() / fp.flat_grad.norm())
+    assert rel < 1e-5, rel
+    # the balanced assignment: same table and costs on both ranks, every view once, same reduced gradients
+    b0 = torch.load(os.path.join(tmp_path, "balanced_0.pt"))
+    b1 = torch.load(os.path.join(tmp_path, "balanced_1.pt"))
+    assert b0["table"] == b1["table"] and b0["costs"] == b1["costs"]
+    assert sorted(v for q in b0["table"] for v in q) == list(range(NV)) and all(c > 0 for c in b0["costs"])
+    assert torch.equal(b0["grad"], b1["grad"])
+    rel = float((b0["grad"] - fp.flat_grad).norm() / fp.flat_grad.norm())
     assert rel < 1e-5, rel
