@@ -591,7 +591,10 @@ def main():
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["alg_GBps"], "peak": peak,
                             "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic,
                             "peak_source": peak_src, "R": R, "V": V,
-                            "note": "blend kernels are FP32-issue/L2-atomic bound, not HBM bound; see stages + profiles/"}
+                            "note": "blend kernels are FP32-issue bound (83-86% of issue slots active), not HBM "
+                                    "bound; see stages + profiles/.  traffic: DRAM bytes of one launch from the "
+                                    "committed ncu --set full capture of bench camera 100 (R = 7.7 M tile instances; "
+                                    "the bench views average the R given here)"}
         pb = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges"]
         t_pb = sum(stages[k]["ms"] for k in pb if k in stages)
         b_pb = ab["preprocess"] + ab["scan"] + ab["duplicate"] + ab["sort"] + ab["ranges"]

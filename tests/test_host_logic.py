@@ -162,3 +162,32 @@ def test_balance_views_equal_cardinality_and_lower_imbalance():
     assert all(len(q) == 4 for q in t) and max(load) / (sum(load) / 8) < 1.01
     with pytest.raises(ValueError):
         VP.balance_views([1.0], 0)
+
+
+def test_bench_helpers():
+    """bench.py without a GPU: the SURVEY section 8d byte model, and the one-JSON-line guard (native libraries that
+    write to file descriptor 1 must not reach the real stdout)."""
+    import textwrap
+    sys.path.insert(0, ROOT)
+    import bench
+    # SURVEY 8d example: C3 with V = 0.8 M, R = 8 M, N = 2.07 M -> 3.44 GB per view, total formula
+    P, V, R, N, Tt = 1_000_000, 800_000, 8_000_000, 1920 * 1080, 120 * 68
+    ab = bench.algorithmic_bytes(P, V, R, N, Tt)
+    assert sum(ab.values()) == 332 * P + (238 + 24 * 16) * V + 312 * R + 56 * N + 8 * Tt
+    assert abs(sum(ab.values()) / 1e9 - 3.44) < 0.03
+    code = textwrap.dedent(f'''
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import bench
+        bench.guard_stdout()
+        os.write(1, b"NCCL version banner\\\\n")
+        print("python print")
+        bench.emit({{"ok": 1}})
+    ''')
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.stdout == '{"ok": 1}' + chr(10)
+    assert "NCCL version banner" in r.stderr and "python print" in r.stderr
+    # no CUDA device here: bench.py must say so in its one line and fail, never fall back to a CPU path
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")], capture_output=True, text=True)
+        assert r.returncode != 0 and r.stdout.count(chr(10)) == 1 and "no CUDA device" in r.stdout
