@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--config", default="C3", choices=sorted(S.CONFIGS))
     ap.add_argument("--views-per-gpu", type=int, default=4)
     ap.add_argument("--P", type=int, default=0, help="override the Gaussian count of the config (C5 sweep)")
-    ap.add_argument("--repeats", type=int, default=3, help="timed regions of --steps steps; the fastest is reported")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps; the fastest is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-grad-sinks", action="store_true",
