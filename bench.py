@@ -5,12 +5,20 @@
 
 Contract (see DESIGN.md "Measurement"): a step = one training iteration over `views_per_gpu` views per GPU
 (weak scaling): every view is rendered forward and back-propagated through the public GaussianRasterizer API, the
-Gaussian-parameter gradients accumulate in one flat buffer and (N>1) are summed with one NCCL all-reduce.
+Gaussian-parameter gradients accumulate in one flat buffer and (N>1) are summed with NCCL.
 `value` = views/s with the upstream image gradients resident in HBM; `e2e` = the same through host buffers: each
-view's 8-bit ground-truth image comes from pinned host memory (H2D on a copy stream, prefetched one view ahead), is
-and the L1 loss is computed on the device (ours: bags_loss.l1_loss_u8, loss + gradient against the 8-bit image in
-one kernel; reference arm and --torch-loss: uint8 -> fp32 / 255 and the torch operator sequence of
-utils/loss_utils.py:18-19) and read back (D2H) inside the timed region.  Prints ONE JSON line on rank 0.
+view's 8-bit ground-truth image comes from pinned host memory (H2D on a copy stream, overlapping the previous step),
+the L1 loss is computed on the device and read back (D2H) inside the timed region.
+
+Our arm (default `--mode graph`): the step's enqueue is captured once in a CUDA graph (bags_view_parallel.CapturedStep
+over the asynchronous forward, diff_gaussian_rasterization.AsyncForward) and replayed with one launch per step.
+`--mode streams` issues the same work eagerly (blocking forward, two streams).  `drop_in` is the record for the
+unchanged caller: ONE view per step through the reference's API exactly as train.py uses it -- blocking forward, one
+stream, gradients accumulated by autograd -- for both arms.
+
+Timing: >= W warm-up steps, then regions of exactly K steps (barrier + synchronize on both sides, CUDA events, max over
+ranks), at least 5 regions / 100 steps / 2 s of them; the MEDIAN region is reported and all are listed.
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -30,21 +38,28 @@ import torch.distributed as dist  # noqa: E402
 
 import bags_synth as S  # noqa: E402
 
-SCALE = 0.004     # median Gaussian scale of the synthetic scenes (gives R/P ~ 8 at 1080p)
+SCALE = 0.004     # median Gaussian scale of the synthetic scenes (gives R/P ~ 5 at 1080p)
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(S.CONFIGS))
     ap.add_argument("--views-per-gpu", type=int, default=4)
     ap.add_argument("--P", type=int, default=0, help="override the Gaussian count of the config (C5 sweep)")
-    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps; the fastest is reported")
+    ap.add_argument("--scale", type=float, default=SCALE,
+                    help="median Gaussian scale; 0.012 is the blend-heavy scene (R/P ~ 50 at 1080p)")
+    ap.add_argument("--repeats", type=int, default=5, help="minimum number of timed regions of --steps steps")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="minimum total time of the timed regions of a leg")
+    ap.add_argument("--mode", default="graph", choices=["graph", "streams"],
+                    help="our arm: graph = the step captured in a CUDA graph over the asynchronous forward (default); "
+                         "streams = eager launches, blocking forward, views pipelined over --streams CUDA streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-drop-in", action="store_true")
     ap.add_argument("--no-grad-sinks", action="store_true",
                     help="let autograd accumulate the Gaussian gradients (fresh tensors + adds) instead of the "
                          "kernel adding into the flat gradient buffer")
@@ -53,15 +68,12 @@ def parse():
                          "k's preprocess/binning/forward overlaps view k-1's backward; 1 = everything on one stream")
     ap.add_argument("--no-balance", action="store_true",
                     help="N > 1: keep the round-robin view assignment instead of balancing it by tile instances")
-    ap.add_argument("--step-sync", action="store_true",
-                    help="development: host-synchronize at the end of every device-leg step")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: one all-reduce after the step instead of the overlapped schedule")
     ap.add_argument("--torch-loss", action="store_true",
                     help="e2e leg of our arm: the torch operator sequence of utils/loss_utils.py:18-19 (what the "
-                         "reference arm always runs) instead of bags_loss.l1_loss_u8 (loss + gradient against the "
-                         "8-bit ground truth in one kernel)")
-    ap.add_argument("--trace", default="", help="development: write a GPU timeline summary of 2 device-leg and 2 "
-                                                "e2e steps (torch.profiler) to this JSON file; not a bench value")
-    return ap.parse_args()
+                         "reference arm always runs) instead of bags_loss.l1_loss_u8")
+    return ap.parse_args(argv)
 
 
 def load_impl(name):
@@ -151,6 +163,12 @@ def algorithmic_bytes(P, V, R, N, Tt, K=16):
     }
 
 
+def median(xs):
+    s = sorted(xs)
+    n = len(s)
+    return s[n // 2] if n % 2 else 0.5 * (s[n // 2 - 1] + s[n // 2])
+
+
 def cpu_baseline_sample():
     """float64 host oracle (oracle/raster_oracle.py) fwd+bwd on a bounded sample, all host cores."""
     sys.path.insert(0, ROOT)
@@ -175,47 +193,6 @@ def cpu_baseline_sample():
     return {"value": n / dt, "unit": "views/s", "cores": os.cpu_count() or 1, "kind": "port",
             "sample": f"float64 PyTorch host oracle, {P} Gaussians SH3 at {W}x{H}, R={f['num_rendered']}, "
                       f"{n} fwd+bwd views in {dt:.1f}s (NOT the bench workload: a bounded sample)"}
-
-
-def trace_steps(fns, path):
-    """Development aid: GPU busy time, span and the kernels of 2 steps of each leg (CUPTI via torch.profiler)."""
-    from collections import defaultdict
-    from torch.profiler import ProfilerActivity, profile
-    out = {}
-    for name, fn in fns.items():
-        fn()
-        torch.cuda.synchronize()
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            t0 = time.time()
-            for _ in range(2):
-                fn()
-            t_cpu = time.time() - t0
-            torch.cuda.synchronize()
-            t_wall = time.time() - t0
-        tmp = path + ".chrome.json"
-        prof.export_chrome_trace(tmp)
-        tr = json.load(open(tmp))
-        os.remove(tmp)
-        ev = [e for e in tr["traceEvents"] if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
-        ev.sort(key=lambda e: e["ts"])
-        busy = sum(e["dur"] for e in ev)
-        span = (ev[-1]["ts"] + ev[-1]["dur"] - ev[0]["ts"]) if ev else 0
-        agg = defaultdict(lambda: [0, 0.0])
-        for e in ev:
-            a = agg[e["name"][:60]]
-            a[0] += 1
-            a[1] += e["dur"]
-        gaps = []
-        for a, b in zip(ev[:-1], ev[1:]):
-            g = b["ts"] - (a["ts"] + a["dur"])
-            if g > 20:
-                gaps.append({"after": a["name"][:40], "before": b["name"][:40], "us": round(g, 1)})
-        gaps.sort(key=lambda g: -g["us"])
-        out[name] = {"steps": 2, "gpu_busy_us": round(busy, 1), "gpu_span_us": round(span, 1),
-                     "cpu_issue_s": round(t_cpu, 5), "wall_s": round(t_wall, 5),
-                     "top": sorted(([k, v[0], round(v[1], 1)] for k, v in agg.items()), key=lambda r: -r[2])[:40],
-                     "gaps_over_20us": gaps[:40], "gap_total_us": round(sum(g["us"] for g in gaps), 1)}
-    json.dump(out, open(path, "w"), indent=1)
 
 
 _REAL_STDOUT = None
@@ -248,14 +225,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
+    ours = args.impl == "ours"
+    if not ours and rank != 0:
         return 0
     if not torch.cuda.is_available():
         emit({"error": "no CUDA device: bench.py measures the CUDA path and has no CPU fallback"})
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    use_dist = world > 1 and args.impl == "ours"
+    use_dist = world > 1 and ours
     if use_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its debug output (the image sets NCCL_DEBUG=VERSION: a version banner) to stdout, next to the
@@ -273,20 +251,22 @@ def main():
     P, W, H = args.P or cfg["P"], cfg["W"], cfg["H"]
     N = W * H
     vpg = args.views_per_gpu
-    nviews = vpg * (world if args.impl == "ours" else 1)
-    my_views = list(range(rank, nviews, world)) if args.impl == "ours" else list(range(nviews))
+    nviews = vpg * (world if ours else 1)
+    my_views = list(range(rank, nviews, world)) if ours else list(range(nviews))
+    graph_mode = ours and args.mode == "graph"
 
     # ---- scene: replicated Gaussians (seed 0, placed in front of camera 100), one camera per view (seed 100+v) -------
     cam0 = S.make_camera(W, H, seed=100)
-    gs = S.make_gaussians(P, cam0, seed=0, scale=SCALE)
+    gs = S.make_gaussians(P, cam0, seed=0, scale=args.scale)
     import bags_view_parallel as VP
     params = VP.FlatGaussianParams(gs.means3D.to(dev), gs.shs.to(dev), gs.opacities.to(dev), gs.scales.to(dev),
                                    gs.rotations.to(dev), device=dev)
-    grad_sinks = args.impl == "ours" and not args.no_grad_sinks
+    grad_sinks = ours and not args.no_grad_sinks
     if grad_sinks:
-        params.enable_direct_accumulation(mod)
+        params.enable_direct_accumulation(mod)     # consulted only inside `with params.accumulating()`
     bg = torch.zeros(3, device=dev)
     shift = torch.zeros(3, device=dev, requires_grad=True)
+
     def make_view(v):
         cam = S.make_camera(W, H, seed=100 + v)
         g = torch.Generator().manual_seed(1000 + v)
@@ -296,7 +276,7 @@ def main():
         return dict(
             id=v, view=cam.viewmatrix.to(dev).requires_grad_(True), proj=cam.projmatrix.to(dev).requires_grad_(True),
             campos=cam.campos.to(dev).requires_grad_(True), intrinsic=cam.intrinsic.to(dev), cam=cam,
-            gt_host=gt_host, gt_dev=torch.empty(3, H, W, device=dev, dtype=torch.uint8), up=up)
+            gt_host=gt_host, gt_dev=[torch.empty(3, H, W, device=dev, dtype=torch.uint8) for _ in range(2)], up=up)
 
     views = [make_view(v) for v in my_views]
 
@@ -311,6 +291,11 @@ def main():
         return rast(means3D=params["means3D"], means2D=m2d, means2D_densify=m2dd, shift_factors=shift,
                     opacities=params["opacities"], shs=params["shs"], scales=params["scales"],
                     rotations=params["rotations"])
+
+    def clear_pose_grads():
+        for vw in views:
+            vw["view"].grad = vw["proj"].grad = vw["campos"].grad = None
+        shift.grad = None
 
     # ---- view -> rank assignment balanced by measured work (N > 1) -----------------------------------------------
     # The step time of view-parallel training is the time of the slowest rank, and the tile-instance count of the
@@ -340,97 +325,209 @@ def main():
             views = [make_view(v) for v in my_views]
         torch.cuda.empty_cache()
 
-    pipe = VP.ViewStreams(dev, depth=args.streams if args.impl == "ours" else 1)
+    # ---- workload statistics: visible Gaussians V and tile instances R of every view of this rank (blocking forward) --
+    Vs, Rs = [], []
+    with torch.no_grad():
+        for vw in views:
+            c, radii, d, w_, _ = render(vw)
+            Vs.append(int((radii > 0).sum()))
+            del c, radii, d, w_
+    for vw in views:
+        c = render(vw)[0]
+        Rs.append(int(c.grad_fn.num_rendered))
+        del c
+    V = sum(Vs) / len(Vs)
+    R = sum(Rs) / len(Rs)
+    capacity = int(max(Rs) * 1.25) + (64 << 10)
+
+    pipe = VP.ViewStreams(dev, depth=args.streams if ours else 1)
     pipe_serial = VP.ViewStreams(dev, depth=1)
 
-    def step_device(pipe=pipe):
-        """upstream gradients resident in HBM"""
-        params.zero_grad()
-        pipe.begin()
-        for k, vw in enumerate(views):
-            with pipe.view(k):
-                color, radii, depth, weights, _ = render(vw)
-                pipe.before_backward()
-                torch.autograd.backward([color, depth, weights], vw["up"])
-                pipe.after_backward()
-        pipe.end()
-        if use_dist:
-            VP.allreduce_gradients(params)
-        if args.step_sync:
-            torch.cuda.current_stream().synchronize()
-
-    copy_stream = torch.cuda.Stream(device=dev)
     l1_loss_u8 = None
-    if args.impl == "ours" and not args.torch_loss:
+    if ours and not args.torch_loss:
         import bags_loss          # l1_loss against the 8-bit ground truth as stored: loss + gradient in one kernel
         l1_loss_u8 = bags_loss.l1_loss_u8
-        l1_loss = None
-    else:
-        def l1_loss(network_output, gt):   # utils/loss_utils.py:18-19, the operator sequence the reference runs
-            return torch.abs(network_output - gt).mean()
 
-    def issue_h2d(vw):
-        """host->device copy of one view's ground truth on the copy stream (after the previous reader of the buffer)"""
-        with torch.cuda.stream(copy_stream):
-            if vw.get("used_ev") is not None:
-                copy_stream.wait_event(vw["used_ev"])
-            vw["gt_dev"].copy_(vw["gt_host"], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return ev
+    def l1_loss(network_output, gt):   # utils/loss_utils.py:18-19, the operator sequence the reference runs
+        return torch.abs(network_output - gt).mean()
 
-    def step_e2e():
-        """ground-truth image from pinned host memory (H2D every view, prefetched one view ahead on a copy stream so
-        that it overlaps the previous view's kernels), L1 loss on the device, loss read back"""
+    def view_loss(color, gt_u8):
+        if l1_loss_u8 is not None:
+            return l1_loss_u8(color, gt_u8)
+        return l1_loss(color, gt_u8.float().mul_(1.0 / 255.0))
+
+    # ---- the step, as an enqueue ------------------------------------------------------------------------------------
+    def body_device(p=None):
+        """all views of the step: forward + backward with the upstream gradients resident in HBM"""
+        p = p or pipe
+        params.zero_grad()
+        with params.accumulating():
+            p.begin()
+            for k, vw in enumerate(views):
+                with p.view(k):
+                    color, radii, depth, weights, _ = render(vw)
+                    p.before_backward()
+                    torch.autograd.backward([color, depth, weights], vw["up"])
+                    p.after_backward()
+            p.end()
+
+    loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
+
+    def body_e2e(buf):
+        """the same with the L1 loss against the 8-bit ground truth in gt_dev[buf]; the step's loss goes to loss_dev[buf]"""
         params.zero_grad()
         losses = []
-        pipe.begin()
-        ev_next = issue_h2d(views[0])
-        for k, vw in enumerate(views):
-            ev = ev_next
-            if k + 1 < len(views):
-                ev_next = issue_h2d(views[k + 1])
-            with pipe.view(k):
-                cur = torch.cuda.current_stream()
-                color, radii, depth, weights, _ = render(vw)
-                cur.wait_event(ev)
-                if l1_loss_u8 is not None:
-                    loss = l1_loss_u8(color, vw["gt_dev"])
-                else:
-                    loss = l1_loss(color, vw["gt_dev"].float().mul_(1.0 / 255.0))
-                pipe.before_backward()
-                loss.backward()
-                pipe.after_backward()
-                used = torch.cuda.Event()
-                used.record(cur)
-                vw["used_ev"] = used
-                losses.append(loss.detach())
-        pipe.end()
+        with params.accumulating():
+            pipe.begin()
+            for k, vw in enumerate(views):
+                with pipe.view(k):
+                    color, radii, depth, weights, _ = render(vw)
+                    loss = view_loss(color, vw["gt_dev"][buf])
+                    pipe.before_backward()
+                    loss.backward()
+                    pipe.after_backward()
+                    losses.append(loss.detach())
+            pipe.end()
+        loss_dev[buf].copy_(torch.stack(losses).sum().reshape(1))
+
+    capi = None
+    if ours:
+        import bags_capi as capi
+    launches_per_step = None
+    cap_dev = cap_e2e = None
+    if graph_mode:
+        clear_pose_grads()
+        cap_dev = VP.CapturedStep(body_device, dev, mod, capacity, forwards_per_step=len(views))
+        # kernels of ours inside one step (what one replay launches): counted on an eager run of the same enqueue
+        with mod.AsyncForward(capacity, slots=len(views)):
+            l0 = capi.lib().bags_launch_count()
+            body_device()
+            launches_per_step = int(capi.lib().bags_launch_count() - l0)
+        torch.cuda.synchronize()
+        clear_pose_grads()
+
+    overlap = None
+    if use_dist:
+        overlap = None if args.no_overlap else VP.GradientReducer(params)
+
+    def reduce_grads():
         if use_dist:
-            VP.allreduce_gradients(params)
-        # device->host read of the step's loss, every step: an asynchronous copy into pinned memory whose value the
-        # host picks up one step later (how a training loop logs its loss without draining the GPU every iteration);
-        # finish_e2e() collects the last one inside the timed region
-        slot = loss_slots[step_e2e.n % 2]
+            if overlap is not None:
+                overlap.reduce()
+            else:
+                VP.allreduce_gradients(params)
+
+    def step_device():
+        if cap_dev is not None:
+            cap_dev.replay()
+        else:
+            body_device()
+        reduce_grads()
+
+    # ---- e2e: ground truth from pinned host memory, loss read back ------------------------------------------------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    st8 = {"n": 0, "h2d": [None, None], "used": [None, None], "last_loss": None}
+    loss_slots = [{"host": torch.zeros(1, dtype=torch.float32).pin_memory(), "ev": None} for _ in range(2)]
+
+    def issue_h2d(buf):
+        """host->device copies of every view's ground truth into buffer set `buf` on the copy stream, after the last
+        step that read that set"""
+        with torch.cuda.stream(copy_stream):
+            if st8["used"][buf] is not None:
+                copy_stream.wait_event(st8["used"][buf])
+            for vw in views:
+                vw["gt_dev"][buf].copy_(vw["gt_host"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        st8["h2d"][buf] = ev
+
+    def step_e2e():
+        """The step with host-resident ground truth.  Two device buffer sets alternate: the copies for step s+1 run on
+        the copy stream underneath step s.  The step's loss is copied to pinned host memory every step and consumed
+        one step later (how a training loop logs its loss without draining the GPU); finish_e2e() collects the last
+        one inside the timed region."""
+        buf = st8["n"] % 2
+        if st8["h2d"][buf] is None:
+            issue_h2d(buf)
+        issue_h2d(1 - buf)                                  # next step's images
+        cur = torch.cuda.current_stream()
+        cur.wait_event(st8["h2d"][buf])
+        if cap_e2e is not None:
+            cap_e2e[buf].replay()
+        else:
+            body_e2e(buf)
+        used = torch.cuda.Event()
+        used.record(cur)
+        st8["used"][buf] = used
+        st8["h2d"][buf] = None
+        reduce_grads()
+        slot = loss_slots[st8["n"] % 2]
         if slot["ev"] is not None:
             slot["ev"].synchronize()
-            step_e2e.last_loss = float(slot["host"][0])
-        slot["host"].copy_(torch.stack(losses).sum().reshape(1), non_blocking=True)
+            st8["last_loss"] = float(slot["host"][0])
+        slot["host"].copy_(loss_dev[buf], non_blocking=True)
         slot["ev"] = torch.cuda.Event()
         slot["ev"].record()
-        step_e2e.n += 1
-
-    loss_slots = [{"host": torch.zeros(1, dtype=torch.float32).pin_memory(), "ev": None} for _ in range(2)]
-    step_e2e.n = 0
-    step_e2e.last_loss = None
+        st8["n"] += 1
 
     def finish_e2e():
         for slot in loss_slots:
             if slot["ev"] is not None:
                 slot["ev"].synchronize()
-                step_e2e.last_loss = float(slot["host"][0])
+                st8["last_loss"] = float(slot["host"][0])
                 slot["ev"] = None
 
+    # ---- drop-in record: ONE view per step through the API exactly as train.py uses it ----------------------------------
+    dstate = {"n": 0, "ev_next": None, "last_loss": None}
+    d_slots = [{"host": torch.zeros(1, dtype=torch.float32).pin_memory(), "ev": None} for _ in range(2)]
+
+    def h2d_one(vw):
+        with torch.cuda.stream(copy_stream):
+            if vw.get("used_ev") is not None:
+                copy_stream.wait_event(vw["used_ev"])
+            vw["gt_dev"][0].copy_(vw["gt_host"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def step_dropin_device():
+        vw = views[dstate["n"] % len(views)]
+        params.zero_grad()
+        color, radii, depth, weights, _ = render(vw)          # blocking forward, current stream, no sinks
+        torch.autograd.backward([color, depth, weights], vw["up"])
+        dstate["n"] += 1
+
+    def step_dropin_e2e():
+        k = dstate["n"] % len(views)
+        vw = views[k]
+        ev = dstate["ev_next"] or h2d_one(vw)
+        dstate["ev_next"] = h2d_one(views[(k + 1) % len(views)])      # prefetch the next view's image
+        params.zero_grad()
+        cur = torch.cuda.current_stream()
+        color, radii, depth, weights, _ = render(vw)
+        cur.wait_event(ev)
+        loss = l1_loss(color, vw["gt_dev"][0].float().mul_(1.0 / 255.0))   # the caller's own torch loss
+        loss.backward()
+        used = torch.cuda.Event()
+        used.record(cur)
+        vw["used_ev"] = used
+        slot = d_slots[dstate["n"] % 2]
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()
+            dstate["last_loss"] = float(slot["host"][0])
+        slot["host"].copy_(loss.detach().reshape(1), non_blocking=True)
+        slot["ev"] = torch.cuda.Event()
+        slot["ev"].record()
+        dstate["n"] += 1
+
+    def finish_dropin():
+        for slot in d_slots:
+            if slot["ev"] is not None:
+                slot["ev"].synchronize()
+                dstate["last_loss"] = float(slot["host"][0])
+                slot["ev"] = None
+
+    # ---- timing ---------------------------------------------------------------------------------------------------------
     def barrier():
         if use_dist:
             dist.barrier()
@@ -454,20 +551,17 @@ def main():
         return ms
 
     def timed(fn, steps, finish=None):
-        """`--repeats` timed regions of exactly `steps` steps each (barrier + synchronize on both sides, CUDA events,
-        max over ranks); the fastest region is reported and all of them are listed in the JSON line.  The host side
-        of a step is a few hundred microseconds of Python per view: a single region is exposed to whatever else the
-        box's CPUs are doing."""
-        all_ms = [timed_once(fn, steps, finish) for _ in range(max(1, args.repeats))]
-        return min(all_ms), all_ms
-
-    capi = None
-    if args.impl == "ours":
-        import bags_capi as capi
+        """Regions of exactly `steps` steps each (barrier + synchronize on both sides, CUDA events, max over ranks): at
+        least --repeats regions, at least 100 steps and at least --min-seconds in total (capped at 40 regions; every
+        rank takes the same decisions because the times are already max-reduced).  The MEDIAN region is reported."""
+        need = max(1, args.repeats, math.ceil(100 / max(1, steps)))
+        all_ms = []
+        while len(all_ms) < need or (sum(all_ms) < 1e3 * args.min_seconds and len(all_ms) < 40):
+            all_ms.append(timed_once(fn, steps, finish))
+        return median(all_ms), all_ms
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    # W untimed warm-up steps, and at least ~1.5 s of them: the first timed region of a run was measured 5-90% slower
-    # than the following ones with only a handful of warm-up steps (allocator growth, clocks, page-locked staging)
+    # W untimed warm-up steps, and at least ~1.5 s of them (allocator growth, clocks, page-locked staging)
     t_warm, n_warm = time.time(), 0
     while n_warm < max(args.warmup, 3) or (time.time() - t_warm < 1.5 and n_warm < 400):
         step_device()
@@ -478,37 +572,60 @@ def main():
     if sampler is not None:
         sampler.wait_first_sample()
 
-    # workload statistics: visible Gaussians V and tile instances R of every view of this rank (means are used
-    # for the algorithmic byte counts, since the stage times below are averages over the same views)
-    Vs, Rs = [], []
-    for vw in views:
-        c, radii, d, w_, _ = render(vw)
-        Vs.append(int((radii > 0).sum()))
-        Rs.append(int(c.grad_fn.num_rendered))
-        del c, radii, d, w_
-    V = sum(Vs) / len(Vs)
-    R = sum(Rs) / len(Rs)
-
     launches = None
-    if capi is not None:
+    if capi is not None and not graph_mode:
         launches0 = capi.lib().bags_launch_count()
     ms, ms_all = timed(step_device, args.steps)
     if capi is not None:
-        # launches of one timed region (all regions run the same steps)
-        launches = int(capi.lib().bags_launch_count() - launches0) // max(1, args.repeats)
+        if graph_mode:
+            launches = launches_per_step * args.steps          # one replay = the captured launches of one step
+        else:
+            launches = int(capi.lib().bags_launch_count() - launches0) // len(ms_all)
+    if cap_dev is not None:
+        cap_dev.check()
 
     e2e = None
     if not args.no_e2e:
+        if graph_mode:
+            clear_pose_grads()
+            cap_e2e = [VP.CapturedStep(lambda b=b: body_e2e(b), dev, mod, capacity, forwards_per_step=len(views))
+                       for b in range(2)]
         for _ in range(max(args.warmup, 3)):
             step_e2e()
         finish_e2e()
         ms_e2e, ms_e2e_all = timed(step_e2e, args.steps, finish_e2e)
+        if cap_e2e is not None:
+            for c in cap_e2e:
+                c.check()
         e2e = {"value": nviews * args.steps / (ms_e2e / 1e3), "unit": "views/s",
                "h2d_bytes_per_step": len(views) * 3 * N, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps,
                "ms_per_step_regions": [round(m / args.steps, 4) for m in ms_e2e_all],
                "loss_readback": "async copy to pinned memory every step, consumed one step later",
-               "last_loss": step_e2e.last_loss}
+               "last_loss": st8["last_loss"]}
+
+    # ---- drop-in record (N = 1): one view per step, blocking forward, one stream, autograd accumulation -----------------
+    drop_in = None
+    if world == 1 and not args.no_drop_in:
+        nsteps = args.steps * len(views)                       # every camera equally often in a region
+        for _ in range(2 * len(views)):
+            step_dropin_device()
+        d_ms, d_all = timed(step_dropin_device, nsteps)
+        drop_in = {"value": nsteps / (d_ms / 1e3), "unit": "views/s", "ms_per_view": d_ms / nsteps,
+                   "ms_per_view_regions": [round(m / nsteps, 4) for m in d_all],
+                   "what": "ONE view per step through GaussianRasterizer exactly as train.py calls it: blocking "
+                           "forward, current stream, gradients accumulated by autograd (no sinks, no graph, no "
+                           "view pipelining); same cameras, upstream gradients resident in HBM"}
+        if not args.no_e2e:
+            for _ in range(2 * len(views)):
+                step_dropin_e2e()
+            finish_dropin()
+            de_ms, de_all = timed(step_dropin_e2e, nsteps, finish_dropin)
+            drop_in["e2e"] = {"value": nsteps / (de_ms / 1e3), "unit": "views/s", "ms_per_view": de_ms / nsteps,
+                              "ms_per_view_regions": [round(m / nsteps, 4) for m in de_all],
+                              "h2d_bytes_per_step": 3 * N, "d2h_bytes_per_step": 4,
+                              "what": "+ 8-bit ground truth from pinned host memory (prefetched one view ahead), "
+                                      "torch L1 loss (utils/loss_utils.py:18-19), loss read back"}
     clocks = sampler.stop() if sampler is not None else None
 
     # per-stage CUDA-event times (events on the launching stream, recorded inside the library) in a separate short
@@ -518,13 +635,10 @@ def main():
         capi.lib().bags_profile_enable(1)
         capi.profile_read()
         for _ in range(3):
-            step_device(pipe_serial)       # one stream: concurrent kernels would inflate each other's event times
+            body_device(pipe_serial)       # one stream: concurrent kernels would inflate each other's event times
         torch.cuda.synchronize()
         stage_ms, stage_calls = capi.profile_read()
         capi.lib().bags_profile_enable(0)
-
-    if args.trace and rank == 0:
-        trace_steps({"device": step_device, "e2e": step_e2e}, args.trace)
 
     if rank != 0:
         if use_dist:
@@ -534,32 +648,46 @@ def main():
     value = nviews * args.steps / (ms / 1e3)
     line = {
         "metric": "fwd+bwd views/s (1M Gaussians, 1080p)" if args.config == "C3" else f"fwd+bwd views/s ({args.config})",
-        "value": value, "unit": "views/s", "n_gpus": world if args.impl == "ours" else 1, "steps": args.steps,
+        "value": value, "unit": "views/s", "n_gpus": world if ours else 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "ms_per_step_regions": [round(m / args.steps, 4) for m in ms_all], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step_regions": [round(m / args.steps, 4) for m in ms_all], "region_statistic": "median",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {P} random Gaussians SH3, {W}x{H}, {vpg} views/GPU/step "
-                               f"(fwd+bwd incl. pose/intrinsic grads), median scale {SCALE}",
-                   "views_per_step": nviews, "visible_mean": V, "tile_instances_mean": R, "l2": "per-view working set (236 B x P inputs + state) "
-                   "exceeds the 126 MB L2; no explicit flush", "parallelism": f"view-dp{world}",
-                   "view_assignment": assignment, "streams": pipe.depth,
-                   "grad_accumulation": "kernel adds into the flat gradient buffer (register_grad_sink)" if grad_sinks
-                   else "autograd (fresh gradient tensors + add)"},
+                               f"(fwd+bwd incl. pose/intrinsic grads), median scale {args.scale}",
+                   "l2": "per-view working set (236 B x P inputs + state) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": f"view-dp{args.gpus}"},
+        "workload_stats": {"views_per_step": nviews, "visible_mean": V, "tile_instances_mean": R},
         "clocks": clocks,
     }
-    if args.impl == "reference":
+    if not ours:
         line["impl"] = "reference"
+        line["implementation"] = {"mode": "eager, blocking forward (the reference's cudaMemcpy), one stream, autograd "
+                                          "accumulation"}
         line["cpu_baseline"] = {"value": value, "unit": "views/s", "cores": 0, "kind": "reference",
                                 "sample": "the reference has no CPU rasterizer: this arm times its unmodified CUDA "
                                           "extension (oracle/_ref, built for sm_100) through its own Python API on "
                                           "the same workload, GPU-resident inputs"}
         line["e2e"] = {"value": e2e["value"] if e2e else value, "unit": "views/s",
                        "h2d_bytes_per_step": e2e["h2d_bytes_per_step"] if e2e else 0,
-                       "d2h_bytes_per_step": e2e["d2h_bytes_per_step"] if e2e else 0}
+                       "d2h_bytes_per_step": e2e["d2h_bytes_per_step"] if e2e else 0,
+                       "ms_per_step_regions": e2e["ms_per_step_regions"] if e2e else None}
+        if drop_in is not None:
+            line["drop_in"] = drop_in
         emit(line)
         return 0
 
+    line["implementation"] = {
+        "mode": ("CUDA graph of the step's enqueue (bags_view_parallel.CapturedStep) over the asynchronous forward "
+                 f"(binning capacity {capacity} tile instances), one launch per step") if graph_mode
+        else "eager launches, blocking forward",
+        "streams": pipe.depth, "view_assignment": assignment,
+        "grad_accumulation": "kernel adds into the flat gradient buffer (register_grad_sink)" if grad_sinks
+        else "autograd (fresh gradient tensors + add)",
+        "allreduce": (overlap.describe() if overlap is not None else "one all_reduce after the step") if use_dist
+        else None}
     line["e2e"] = e2e
+    if drop_in is not None:
+        line["drop_in"] = drop_in
     line["gpu_launches"] = launches
     # ---- roofline of the dominant kernel + per-stage table -----------------------------------------------------
     peaks = {}
@@ -582,19 +710,21 @@ def main():
         stages[k] = {"ms": round(avg, 4), "alg_GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
     dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
     traffic = None
+    traffic_R = None
     try:  # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        traffic_R = tj.get("_meta", {}).get("tile_instances")
     except Exception:
         pass
     if dom:
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["alg_GBps"], "peak": peak,
                             "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic,
                             "peak_source": peak_src, "R": R, "V": V,
-                            "note": "blend kernels are FP32-issue bound (83-86% of issue slots active), not HBM "
-                                    "bound; see stages + profiles/.  traffic: DRAM bytes of one launch from the "
-                                    "committed ncu --set full capture of bench camera 100 (R = 7.7 M tile instances; "
-                                    "the bench views average the R given here)"}
+                            "note": "blend kernels are FP32-issue bound, not HBM bound; see stages + profiles/.  "
+                                    "traffic: DRAM bytes of one launch from the committed ncu --set full capture "
+                                    f"(one view with R = {traffic_R} tile instances; the bench views average the R "
+                                    "given here)"}
         pb = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges"]
         t_pb = sum(stages[k]["ms"] for k in pb if k in stages)
         b_pb = ab["preprocess"] + ab["scan"] + ab["duplicate"] + ab["sort"] + ab["ranges"]

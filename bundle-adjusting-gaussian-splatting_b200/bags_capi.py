@@ -31,6 +31,11 @@ SIGNATURES = {
                                        c_float, c_float, c_int,                      # tanfovx, tanfovy, prefiltered
                                        _P, _P, _P, _P, _P, _P,                       # color, depth, alpha, radii, m2Dx, m2Dy
                                        c_int, _P]),                                  # debug, stream
+    "bags_rasterize_forward_async": (c_int, [ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P, c_int, c_int, c_int,
+                                             _P, c_int, c_int, _P, _P, _P, _P, _P, c_float, _P, _P,
+                                             _P, _P, _P, _P, _P, c_float, c_float, c_int,
+                                             _P, _P, _P, _P, _P, _P,
+                                             c_int, _P, _P]),                        # capacity, count out, stream
     "bags_rasterize_backward": (c_int, [c_int, c_int, c_int, c_int,                  # P, D, M, R
                                         _P, c_int, c_int,                            # background, width, height
                                         _P, _P, _P, _P,                              # means3D, shs, colors, alphas

@@ -31,6 +31,8 @@ class _L1SSIM(torch.autograd.Function):
         planes = a.numel() // (H * W)
         need_grad = ctx.needs_input_grad[0]
         maps = torch.empty((3, planes, H, W), dtype=torch.float32, device=dev) if (need_grad and want_ssim) else None
+        if img2.dtype != img1.dtype and ctx.needs_input_grad[1]:
+            raise RuntimeError("loss: img1 and img2 must share a dtype when both require gradients")
         L = capi.lib()
         scratch = torch.empty((int(L.bags_loss_scratch_bytes(planes, H, W)),), dtype=torch.uint8, device=dev)
         sums = torch.empty((planes, 2), dtype=torch.float64, device=dev)
@@ -44,6 +46,7 @@ class _L1SSIM(torch.autograd.Function):
         capi.check(rc, "bags_loss_forward")
         ctx.save_for_backward(a, b, maps if maps is not None else torch.empty(0, device=dev))
         ctx.meta = (planes, H, W, bool(want_ssim), img1.shape, img1.dtype)
+        ctx.scratch_bytes = scratch.numel()
         return sums[:, 0].clone(), sums[:, 1].clone()
 
     @staticmethod
@@ -54,15 +57,43 @@ class _L1SSIM(torch.autograd.Function):
         coef = torch.stack([g_l1.to(torch.float32), g_ssim.to(torch.float32)], dim=1).contiguous()   # [planes, 2]
         out = torch.empty_like(a)
         has_maps = maps.numel() > 0
-        with torch.cuda.device(dev):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            rc = capi.lib().bags_loss_backward(_ptr(a), _ptr(b), planes, H, W,
-                                               _ptr(maps[0]) if has_maps else ctypes.c_void_p(0),
-                                               _ptr(maps[1]) if has_maps else ctypes.c_void_p(0),
-                                               _ptr(maps[2]) if has_maps else ctypes.c_void_p(0),
-                                               _ptr(coef), _ptr(out), stream)
+        rc = 0
+        if ctx.needs_input_grad[0]:
+            with torch.cuda.device(dev):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                rc = capi.lib().bags_loss_backward(_ptr(a), _ptr(b), planes, H, W,
+                                                   _ptr(maps[0]) if has_maps else ctypes.c_void_p(0),
+                                                   _ptr(maps[1]) if has_maps else ctypes.c_void_p(0),
+                                                   _ptr(maps[2]) if has_maps else ctypes.c_void_p(0),
+                                                   _ptr(coef), _ptr(out), stream)
         capi.check(rc, "bags_loss_backward")
-        return out.view(shape).to(dtype), None, None
+        g1 = out.view(shape).to(dtype) if ctx.needs_input_grad[0] else None
+        g2 = None
+        if ctx.needs_input_grad[1]:
+            # The reference's second argument often carries gradients too (apply2gt: the ground truth is a
+            # grid_sample through the lens network; after start_vignetting it is multiplied by a learnable mask).
+            # Both terms are symmetric in their arguments, so the gradient w.r.t. img2 is the same pair of kernels with
+            # the arguments swapped: the forward once more for the three derivative maps taken w.r.t. img2's moments,
+            # then the backward.
+            L = capi.lib()
+            maps2 = torch.empty((3, planes, H, W), dtype=torch.float32, device=dev) if want_ssim else None
+            out2 = torch.empty_like(b)
+            with torch.cuda.device(dev):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                if want_ssim:
+                    scratch = torch.empty((int(ctx.scratch_bytes),), dtype=torch.uint8, device=dev)
+                    sums = torch.empty((planes, 2), dtype=torch.float64, device=dev)
+                    rc = L.bags_loss_forward(_ptr(b), _ptr(a), planes, H, W, 1, _ptr(maps2[0]), _ptr(maps2[1]),
+                                             _ptr(maps2[2]), _ptr(scratch), _ptr(sums), stream)
+                    capi.check(rc, "bags_loss_forward")
+                rc = L.bags_loss_backward(_ptr(b), _ptr(a), planes, H, W,
+                                          _ptr(maps2[0]) if want_ssim else ctypes.c_void_p(0),
+                                          _ptr(maps2[1]) if want_ssim else ctypes.c_void_p(0),
+                                          _ptr(maps2[2]) if want_ssim else ctypes.c_void_p(0),
+                                          _ptr(coef), _ptr(out2), stream)
+            capi.check(rc, "bags_loss_backward")
+            g2 = out2.view(shape).to(dtype)
+        return g1, g2, None
 
 
 def _sums(img1, img2, want_ssim):
@@ -72,7 +103,8 @@ def _sums(img1, img2, want_ssim):
 
 
 def l1_loss(network_output, gt):
-    """utils/loss_utils.py:18-19: mean |network_output - gt| (gradient flows to network_output only)."""
+    """utils/loss_utils.py:18-19: mean |network_output - gt| (gradients flow to both arguments, like the reference's
+    torch expression)."""
     s_l1, _, _ = _sums(network_output, gt, False)
     return (s_l1.sum() / network_output.numel()).to(torch.float32)
 

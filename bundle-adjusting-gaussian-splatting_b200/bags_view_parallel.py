@@ -96,6 +96,7 @@ class FlatGaussianParams:
         self.flat = torch.empty(P * FLOATS_PER_GAUSSIAN, dtype=torch.float32, device=device)
         self.flat_grad = torch.zeros_like(self.flat)
         self.params = {}
+        self.grad_views = {}
         off = 0
         for name, shape in FIELDS:
             n = P
@@ -104,7 +105,8 @@ class FlatGaussianParams:
             view = self.flat[off:off + n].view(P, *shape)
             view.copy_(src[name].reshape(P, *shape))
             p = view.detach().requires_grad_(True)          # leaf sharing storage with the flat buffer
-            p.grad = self.flat_grad[off:off + n].view(P, *shape)
+            self.grad_views[name] = self.flat_grad[off:off + n].view(P, *shape)
+            p.grad = self.grad_views[name]
             self.params[name] = p
             off += n
         assert off == P * FLOATS_PER_GAUSSIAN
@@ -113,7 +115,42 @@ class FlatGaussianParams:
         return self.params[k]
 
     def zero_grad(self):
+        """Zeroes the flat gradient buffer and (re-)attaches every parameter's `.grad` to its slice of it.  Use this
+        instead of `optimizer.zero_grad(set_to_none=True)` (the reference's train.py:421), which drops the `.grad`
+        views: autograd would then allocate fresh gradient tensors outside the flat buffer, and with gradient sinks
+        the kernel would keep adding onto stale sums."""
         self.flat_grad.zero_()
+        for name, p in self.params.items():
+            if p.grad is None or p.grad.data_ptr() != self.grad_views[name].data_ptr():
+                p.grad = self.grad_views[name]
+
+    def ensure_attached(self):
+        """Repairs the `.grad` <-> flat-buffer link after foreign code touched it, keeping the values autograd means:
+        a `.grad` of None (`zero_grad(set_to_none=True)`) stands for zero -> that field's slice is zeroed; a `.grad`
+        that is some other tensor (allocated by autograd after set_to_none) holds the sum accumulated so far -> it is
+        copied into the slice.  Called at the start of `run_views` and by `allreduce_gradients`."""
+        for name, p in self.params.items():
+            view = self.grad_views[name]
+            if p.grad is None:
+                if not getattr(self, "_sink_module", None):
+                    view.zero_()
+                # with direct accumulation the kernel has been adding into the slice while `.grad` was None: the
+                # slice already holds the sum (the step must have started from zero_grad() / ensure_attached())
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+
+    def begin_step(self):
+        """Start of an accumulation step for callers that do not use zero_grad(): `.grad is None` means zero."""
+        for name, p in self.params.items():
+            view = self.grad_views[name]
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
 
     def enable_direct_accumulation(self, rasterizer_module=None):
         """Registers every parameter's gradient view as a gradient sink of the rasterizer
@@ -123,7 +160,7 @@ class FlatGaussianParams:
         if rasterizer_module is None:
             import diff_gaussian_rasterization as rasterizer_module
         for name, _ in FIELDS:
-            rasterizer_module.register_grad_sink(self.params[name], self.params[name].grad)
+            rasterizer_module.register_grad_sink(self.params[name], self.grad_views[name])
         self._sink_module = rasterizer_module
 
     def disable_direct_accumulation(self):
@@ -133,12 +170,105 @@ class FlatGaussianParams:
                 m.unregister_grad_sink(self.params[name])
             self._sink_module = None
 
+    def accumulating(self):
+        """`with params.accumulating():` -- scope in which the registered sinks are active (the training forward +
+        backward of a step).  Outside it -- evaluation renders, torch.autograd.grad probes, double backward -- the
+        rasterizer behaves like the reference: fresh gradient tensors, hooks fire, `.grad` is only touched by
+        autograd."""
+        m = getattr(self, "_sink_module", None)
+        if m is None:
+            import contextlib
+            return contextlib.nullcontext()
+        return m.grad_sinks(True)
+
 
 def allreduce_gradients(params: FlatGaussianParams, group=None, async_op: bool = False):
     """Sums the flat gradient buffer over all ranks (no-op without an initialised process group)."""
+    params.ensure_attached()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
     return dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class GradientReducer:
+    """The step-end sum of the flat gradient buffer over the ranks, plus the small per-step statistics that ride along
+    (SURVEY.md section 8e): everything a view-parallel trainer has to exchange per iteration.
+
+    * `reduce()`: all_reduce(SUM) of `params.flat_grad` (59 floats per Gaussian).
+    * `reduce_stats(stats)`: the densification statistics (scene/gaussian_model.py:449-455: `xyz_gradient_accum`,
+      `xyz_gradient_accum_abs`, `denom` -- per-view norms, so every rank accumulates its own views first and the sums
+      are exchanged once per step), `max_radii2D` (train.py:377: a running maximum -> all_reduce(MAX)) and the gradient
+      of the one global `shift_factors` 3-vector, packed so that the step costs two small collectives next to the big
+      one: one SUM over [accum | accum_abs | denom | shift grad], one MAX over max_radii2D."""
+
+    def __init__(self, params: "FlatGaussianParams", group=None):
+        self.params = params
+        self.group = group
+
+    def describe(self):
+        return "one all_reduce(SUM) of the flat gradient buffer after the step"
+
+    def reduce(self):
+        return allreduce_gradients(self.params, self.group)
+
+    def reduce_stats(self, stats: "DensificationStats", shift_grad=None):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        if shift_grad is not None:
+            stats.sum_buf[-3:].copy_(shift_grad.reshape(3))
+        dist.all_reduce(stats.sum_buf, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(stats.max_radii2D, op=dist.ReduceOp.MAX, group=self.group)
+        if shift_grad is not None:
+            shift_grad.copy_(stats.sum_buf[-3:].view_as(shift_grad))
+
+
+class DensificationStats:
+    """Per-step densification statistics of the views a rank rendered, laid out for one SUM and one MAX collective.
+
+    Mirrors `GaussianModel.add_densification_stats` (scene/gaussian_model.py:449-455) and the `max_radii2D` update of
+    train.py:377: for every view, with vis = radii > 0,
+        xyz_gradient_accum[vis] += ||viewspace_point_tensor.grad[vis, :2]||             (abs_grad False)
+        xyz_gradient_accum[vis] += ||viewspace_point_tensor_densify.grad[vis, :2]||     (abs_grad True)
+        denom[vis]              += 1
+        max_radii2D[vis]         = max(max_radii2D[vis], radii[vis])
+    Both norms are kept (accum / accum_abs) so that the caller picks at `apply_to`.  `sum_buf` = [accum (P) |
+    accum_abs (P) | denom (P) | 3 spare words for the shift_factors gradient]; after `GradientReducer.reduce_stats`
+    every rank holds the step's totals, which the caller adds to the model's running accumulators (`apply_to`)."""
+
+    def __init__(self, P: int, device):
+        self.P = P
+        self.sum_buf = torch.zeros(3 * P + 3, dtype=torch.float32, device=device)
+        self.max_radii2D = torch.zeros(P, dtype=torch.float32, device=device)
+
+    @property
+    def accum(self):
+        return self.sum_buf[:self.P]
+
+    @property
+    def accum_abs(self):
+        return self.sum_buf[self.P:2 * self.P]
+
+    @property
+    def denom(self):
+        return self.sum_buf[2 * self.P:3 * self.P]
+
+    def zero(self):
+        self.sum_buf.zero_()
+        self.max_radii2D.zero_()
+
+    def add_view(self, viewspace_grad, viewspace_grad_densify, radii):
+        vis = radii > 0
+        self.accum.add_(torch.norm(viewspace_grad[:, :2], dim=-1) * vis)
+        self.accum_abs.add_(torch.norm(viewspace_grad_densify[:, :2], dim=-1) * vis)
+        self.denom.add_(vis.to(torch.float32))
+        torch.maximum(self.max_radii2D, radii.to(torch.float32) * vis, out=self.max_radii2D)
+
+    def apply_to(self, xyz_gradient_accum, denom, max_radii2D, abs_grad: bool):
+        """Adds the (reduced) step totals to a GaussianModel's running accumulators (shapes (P,1) / (P,1) / (P,))."""
+        src = self.accum_abs if abs_grad else self.accum
+        xyz_gradient_accum.add_(src.view_as(xyz_gradient_accum))
+        denom.add_(self.denom.view_as(denom))
+        torch.maximum(max_radii2D, self.max_radii2D.view_as(max_radii2D).to(max_radii2D.dtype), out=max_radii2D)
 
 
 def gather_view_costs(local_costs: Sequence[float], num_views: int, rank: int, world: int, group=None) -> List[float]:
@@ -168,10 +298,12 @@ def run_views(params: FlatGaussianParams, views: Sequence, view_loss: Callable, 
     n = len(views) if num_views_total is None else num_views_total
     losses = []
     mine = shard_views(n, rank, world) if assignment is None else list(assignment[rank])
-    for vi in mine:
-        loss = view_loss(params, views[vi])
-        loss.backward()
-        losses.append(loss.detach())
+    params.begin_step()
+    with params.accumulating():
+        for vi in mine:
+            loss = view_loss(params, views[vi])
+            loss.backward()
+            losses.append(loss.detach())
     allreduce_gradients(params, group)
     return losses
 
@@ -248,3 +380,54 @@ class ViewStreams:
                 ev = torch.cuda.Event()
                 ev.record(s)
                 main.wait_event(ev)
+
+
+class CapturedStep:
+    """A training step's whole enqueue -- any number of views: forward, loss, backward, gradient accumulation --
+    captured once in a CUDA graph and replayed with ONE launch per step.
+
+    This is what the asynchronous forward (`diff_gaussian_rasterization.AsyncForward`, C ABI
+    `bags_rasterize_forward_async`) makes possible: the reference blocks the host on a 4-byte copy of `num_rendered` in
+    every forward (rasterizer_impl.cu:291), which can neither be captured nor run ahead of.  With a caller-provided
+    binning capacity a view is a pure enqueue; replayed as a graph, a step costs the host a few microseconds whatever
+    else the machine's CPUs are doing.
+
+        step = CapturedStep(body, device, rasterizer_module, capacity, forwards_per_step=len(views))
+        step.replay()              # every iteration; inputs are updated IN PLACE between replays (static tensors)
+        step.check()               # after a synchronisation point: raises if a view overflowed `capacity`
+
+    `body()` must be capturable: static input tensors (camera matrices, ground truth, parameters are read from fixed
+    addresses -- update them with copy_()), no host synchronisation, gradients of the Gaussian parameters accumulated
+    through gradient sinks or into pre-attached `.grad` buffers.  Per-camera leaves should have `.grad = None` before
+    the capture so that their gradient tensors come from the graph's private pool and are rewritten by every replay.
+    The tile-instance counts of the step's forwards land in `step.counts` (pinned int64[forwards_per_step])."""
+
+    def __init__(self, body: Callable, device, rasterizer_module, capacity: int, forwards_per_step: int,
+                 warmup: int = 2):
+        self.device = torch.device(device)
+        self.af = rasterizer_module.AsyncForward(capacity, slots=max(1, int(forwards_per_step)))
+        self.capacity = int(capacity)
+        main = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):      # eager runs: lazy initialisations happen outside the capture
+                self.af._k = 0
+                with self.af:
+                    body()
+        main.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.af.check()
+        self.graph = torch.cuda.CUDAGraph()
+        self.af._k = 0
+        with torch.cuda.graph(self.graph):
+            with self.af:
+                self.outputs = body()
+        self.counts = self.af.counts
+
+    def replay(self):
+        self.graph.replay()
+
+    def check(self):
+        """Call after the replays of interest have been synchronised: raises on a capacity overflow."""
+        return self.af.check()

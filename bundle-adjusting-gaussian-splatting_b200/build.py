@@ -1,8 +1,9 @@
-"""Builds libbags_b200.so (the C-ABI library) in-tree with nvcc for sm_100a.
+"""Builds, in-tree: libbags_b200.so (the C-ABI library: every CUDA kernel, nvcc for sm_100a) and
+diff_gaussian_rasterization/_C*.so (the thin PyTorch C++ extension above the C ABI, g++ against libtorch).
 
     python bundle-adjusting-gaussian-splatting_b200/build.py [--force] [--verbose]
 
-The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+The .so files are git-ignored but travel to the GPU box with the gpurun snapshot.
 """
 import os
 import subprocess
@@ -27,7 +28,54 @@ def _deps_mtime():
     return m
 
 
+def ext_path():
+    import sysconfig
+    return os.path.join(HERE, "diff_gaussian_rasterization", "_C" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_ext(force=False, verbose=False):
+    """diff_gaussian_rasterization._C: csrc/ext.cpp compiled with g++ against libtorch and linked to libbags_b200.so
+    (found at run time through an $ORIGIN-relative rpath)."""
+    import sysconfig
+    out = ext_path()
+    src = os.path.join(CSRC, "ext.cpp")
+    hdr = os.path.join(HERE, "..", "include", "bags_b200.h")
+    if (not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(hdr))
+            and os.path.getmtime(out) >= os.path.getmtime(LIB)):
+        return out
+    import torch
+    from torch.utils import cpp_extension as ce
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable", src, "-o", out,
+           "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    for inc in ce.include_paths("cuda"):
+        cmd += ["-isystem", inc]
+    cmd += ["-isystem", sysconfig.get_paths()["include"]]
+    cmd += ["-L" + HERE, "-lbags_b200", "-Wl,-rpath,$ORIGIN/..", "-L" + tlib, "-Wl,-rpath," + tlib,
+            "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python"]
+    cuda_lib = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
+    if os.path.isdir(cuda_lib):
+        cmd += ["-L" + cuda_lib]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, "ext.cpp.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for ext.cpp:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
+    lib = build_lib(force, verbose)
+    build_ext(force, verbose)
+    return lib
+
+
+def build_lib(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) > _deps_mtime():
         return LIB
     os.makedirs(OBJ, exist_ok=True)

@@ -7,6 +7,7 @@
 
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 
 namespace bags {
@@ -26,6 +27,7 @@ void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 struct ProfRec { int stage; cudaEvent_t a, b; };
 static bool g_prof_on = false;
+static std::mutex g_prof_mu;             // the hooks may be reached from several host threads
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
 static std::vector<ProfRec> g_prof_open;
@@ -43,6 +45,7 @@ static cudaEvent_t prof_event() {
 
 void prof_begin(int stage, cudaStream_t st) {
     if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfRec r;
     r.stage = stage;
     r.a = prof_event();
@@ -53,6 +56,7 @@ void prof_begin(int stage, cudaStream_t st) {
 
 void prof_end(int stage, cudaStream_t st) {
     if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (size_t i = g_prof_open.size(); i-- > 0;) {
         if (g_prof_open[i].stage == stage) {
             ProfRec r = g_prof_open[i];
@@ -127,28 +131,47 @@ ImageState ImageState::from(char* p, int width, int height) {
     return s;
 }
 
-// ---- per-device host resources: a pinned word for num_rendered and an event --------------------------------------
-struct DeviceCtx {
+// ---- host resources of the synchronous forward: a pinned word for num_rendered and an event per call in flight ------
+// Slots are pooled per device under a mutex and owned by one call at a time, so concurrent forwards from several host
+// threads on one GPU (a viewer or evaluation thread next to the training thread) never share a word or an event.
+struct SyncSlot {
     unsigned long long* pinned = nullptr;
     cudaEvent_t ev = nullptr;
+    int dev = -1;
 };
-static DeviceCtx g_ctx[64];
+static std::mutex g_slot_mu;
+static std::vector<SyncSlot> g_slot_pool;
 
-static int get_ctx(DeviceCtx** out) {
+static int acquire_slot(SyncSlot* out) {
     int dev = 0;
     BAGS_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) {
-        set_error("device index %d out of range", dev);
-        return BAGS_E_INVALID;
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        for (size_t i = 0; i < g_slot_pool.size(); i++) {
+            if (g_slot_pool[i].dev == dev) {
+                *out = g_slot_pool[i];
+                g_slot_pool.erase(g_slot_pool.begin() + i);
+                return 0;
+            }
+        }
     }
-    DeviceCtx& c = g_ctx[dev];
-    if (!c.pinned) {
-        BAGS_CUDA_OK(cudaMallocHost((void**)&c.pinned, 64));
-        BAGS_CUDA_OK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
-    }
-    *out = &c;
+    SyncSlot s;
+    s.dev = dev;
+    BAGS_CUDA_OK(cudaMallocHost((void**)&s.pinned, 64));
+    BAGS_CUDA_OK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    *out = s;
     return 0;
 }
+
+static void release_slot(const SyncSlot& s) {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    g_slot_pool.push_back(s);
+}
+struct SlotGuard {
+    SyncSlot s;
+    bool held = false;
+    ~SlotGuard() { if (held) release_slot(s); }
+};
 
 // ---- unpack kernels (test-only) ----------------------------------------------------------------------------------
 __global__ void unpack_geom_kernel(int P, const float4* __restrict__ rec, const ushort4* __restrict__ rect,
@@ -214,6 +237,7 @@ extern "C" int bags_profile_enable(int on) {
     return 0;
 }
 extern "C" int bags_profile_read(double* ms, unsigned long long* calls) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_prof_recs) {
         BAGS_CUDA_OK(cudaEventSynchronize(r.b));
         float t = 0.f;
@@ -248,25 +272,33 @@ extern "C" size_t bags_backward_scratch_bytes(int P) {
         }                                            \
     } while (0)
 
-extern "C" int bags_rasterize_forward(
+// Shared body of the two forward entry points.
+//   capacity < 0  (bags_rasterize_forward): the reference's protocol -- num_rendered is read back on the host (one
+//                 blocking wait per view, rasterizer_impl.cu:291), the binning buffer has exactly that many slots.
+//   capacity >= 0 (bags_rasterize_forward_async): nothing waits.  The binning buffer, the grids of the emit / tile-sort /
+//                 range kernels and the sort bookkeeping are sized by `capacity`; the kernels read the actual count from
+//                 the geometry state, where the preprocess kernel left it, and clamp it to the capacity.  The count is
+//                 also copied to *count_out (device or pinned host memory) for the caller to look at whenever it likes.
+static int forward_impl(
     bags_alloc_fn geom_alloc, void* geom_user, bags_alloc_fn binning_alloc, void* binning_user,
     bags_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background, int width, int height,
     const float* means3D, const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
     float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
-    const float* projmatrix, const float* intrinsic, const float* cam_pos, const float* shift_factors, float tan_fovx,
-    float tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha, int* radii, float* mean2Dx,
-    float* mean2Dy, int debug, void* stream) {
-    (void)intrinsic;  // passed through by the reference too, never read by live code (forward.cu:352)
-    cudaStream_t st = (cudaStream_t)stream;
+    const float* projmatrix, const float* cam_pos, const float* shift_factors, float tan_fovx, float tan_fovy,
+    int prefiltered, float* out_color, float* out_depth, float* out_alpha, int* radii, float* mean2Dx, float* mean2Dy,
+    int debug, int capacity, unsigned long long* count_out, cudaStream_t st) {
+    const bool async = capacity >= 0;
     BAGS_REQUIRE(P >= 0 && width > 0 && height > 0, "negative P or empty image");
     BAGS_REQUIRE(out_color && out_depth && out_alpha, "null output image");
     BAGS_REQUIRE(geom_alloc && binning_alloc && image_alloc, "null allocation callback");
+    BAGS_REQUIRE(!async || capacity < (1 << 30), "capacity does not fit the 30-bit look-back words");
     const size_t N = (size_t)width * height;
     if (P == 0) {
         // reference: kernels skipped, zero-initialised outputs returned (rasterize_points.cu:66-83)
         BAGS_CUDA_OK(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), st));
         BAGS_CUDA_OK(cudaMemsetAsync(out_depth, 0, N * sizeof(float), st));
         BAGS_CUDA_OK(cudaMemsetAsync(out_alpha, 0, N * sizeof(float), st));
+        if (async && count_out) BAGS_CUDA_OK(cudaMemsetAsync(count_out, 0, sizeof(unsigned long long), st));
         return 0;
     }
     BAGS_REQUIRE(background && means3D && opacities && viewmatrix && projmatrix && cam_pos && shift_factors,
@@ -278,9 +310,13 @@ extern "C" int bags_rasterize_forward(
     BAGS_REQUIRE(shs == nullptr || (M >= (D + 1) * (D + 1) && D >= 0 && D <= 3), "SH degree / coefficient count");
     BAGS_REQUIRE(tiles_x(width) <= 65535 && tiles_y(height) <= 65535, "image too large for 16-bit tile coordinates");
 
-    DeviceCtx* ctx;
-    int rc = get_ctx(&ctx);
-    if (rc) return rc;
+    int rc;
+    SlotGuard slot;
+    if (!async) {
+        rc = acquire_slot(&slot.s);
+        if (rc) return rc;
+        slot.held = true;
+    }
 
     char* geom_ptr = geom_alloc(GeomState::bytes(P), geom_user);
     char* img_ptr = image_alloc(ImageState::bytes(width, height), image_user);
@@ -290,6 +326,18 @@ extern "C" int bags_rasterize_forward(
     }
     GeomState g = GeomState::from(geom_ptr, P);
     ImageState img = ImageState::from(img_ptr, width, height);
+    const int ntiles = tiles_x(width) * tiles_y(height);
+    const int npass = tile_sort_passes(ntiles);
+
+    // Asynchronous mode: everything that could fail on the host is done before the first launch
+    char* bin_ptr = nullptr;
+    if (async) {
+        bin_ptr = binning_alloc(BinningState::bytes(capacity), binning_user);
+        if (!bin_ptr) {
+            set_error("binning allocation callback returned NULL");
+            return BAGS_E_ALLOC;
+        }
+    }
 
     FwdArgs a;
     a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
@@ -301,23 +349,29 @@ extern "C" int bags_rasterize_forward(
     a.focal_x = width / (2.0f * tan_fovx);
     a.prefiltered = prefiltered;
 
-    // counters + emit chained-scan words are contiguous: one memset
-    BAGS_CUDA_OK(cudaMemsetAsync(g.counters, 0, (char*)g.sort.ghist - (char*)g.counters, st));
+    // counters + emit totals + the depth sort's bookkeeping are contiguous: one memset
+    BAGS_CUDA_OK(cudaMemsetAsync(g.counters, 0, ((char*)g.sort.ghist - (char*)g.counters) + g.sort.zero_bytes, st));
     {
         ProfScope ps(BAGS_STAGE_PREPROCESS, st);
         rc = launch_preprocess_fwd(a, g, radii, mean2Dx, mean2Dy, st);
     }
     if (rc) return rc;
 
-    // num_rendered travels to the host while the depth sort runs
-    BAGS_CUDA_OK(cudaMemcpyAsync(ctx->pinned, g.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    BAGS_CUDA_OK(cudaEventRecord(ctx->ev, st));
+    if (async) {
+        if (count_out)
+            BAGS_CUDA_OK(cudaMemcpyAsync(count_out, g.counters, sizeof(unsigned long long), cudaMemcpyDefault, st));
+    } else {
+        // num_rendered travels to the host while the depth sort runs
+        BAGS_CUDA_OK(cudaMemcpyAsync(slot.s.pinned, g.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                     st));
+        BAGS_CUDA_OK(cudaEventRecord(slot.s.ev, st));
+    }
 
     u32 *sorted_keys, *sorted_idx;
     {
         ProfScope ps(BAGS_STAGE_DEPTH_SORT, st);
-        rc = launch_sort_pairs(P, g.key_a, g.idx_a, g.key_b, g.idx_b, 0, 32, g.sort, true, st, &sorted_keys,
-                               &sorted_idx);
+        rc = launch_sort_pairs(P, nullptr, g.key_a, g.idx_a, g.key_b, g.idx_b, 0, 32, g.sort, true, SORT_PREPARED, st,
+                               &sorted_keys, &sorted_idx);
     }
     if (rc) return rc;
 
@@ -329,34 +383,41 @@ extern "C" int bags_rasterize_forward(
     prof_end(BAGS_STAGE_EMIT, st);
     if (rc) return rc;
 
-    BAGS_CUDA_OK(cudaEventSynchronize(ctx->ev));
-    const unsigned long long R64 = *ctx->pinned;
-    if (R64 >= (1ull << 30)) {
-        set_error("num_rendered = %llu does not fit the 30-bit look-back words", R64);
-        return BAGS_E_OVERFLOW;
-    }
-    const int R = (int)R64;
-    const int ntiles = tiles_x(width) * tiles_y(height);
-    const int npass = tile_sort_passes(ntiles);
-
-    char* bin_ptr = binning_alloc(BinningState::bytes(R), binning_user);
-    if (!bin_ptr) {
-        set_error("binning allocation callback returned NULL");
-        return BAGS_E_ALLOC;
+    int R = capacity;                                   // slots of the binning buffer
+    const unsigned long long* R_dev = async ? g.counters : nullptr;
+    if (!async) {
+        BAGS_CUDA_OK(cudaEventSynchronize(slot.s.ev));
+        const unsigned long long R64 = *slot.s.pinned;
+        if (R64 >= (1ull << 30)) {
+            set_error("num_rendered = %llu does not fit the 30-bit look-back words", R64);
+            return BAGS_E_OVERFLOW;
+        }
+        R = (int)R64;
+        bin_ptr = binning_alloc(BinningState::bytes(R), binning_user);
+        if (!bin_ptr) {
+            set_error("binning allocation callback returned NULL");
+            return BAGS_E_ALLOC;
+        }
     }
     BinningState b = BinningState::from(bin_ptr, R, npass);
 
     if (R > 0) {
+        const int hist_passes = npass <= 2 ? npass : 0;     // the fill kernel produces the sort's digit histograms
         {
             ProfScope ps(BAGS_STAGE_EMIT, st);
-            rc = launch_emit_fill(P, R, g, sorted_idx, offsets, b, tiles_x(width), st);
+            if (hist_passes) {
+                rc = sort_prepare(b.sort, st);
+                if (rc) return rc;
+            }
+            rc = launch_emit_fill(P, R, R_dev, g, sorted_idx, offsets, b, tiles_x(width), hist_passes, st);
         }
         if (rc) return rc;
         u32 *fk, *fv;
         {
             ProfScope ps(BAGS_STAGE_TILE_SORT, st);
-            rc = launch_sort_pairs(R, b.tile_buf[0], b.id_buf[0], b.tile_buf[1], b.id_buf[1], 0,
-                                   tile_sort_bits(ntiles), b.sort, false, st, &fk, &fv);
+            rc = launch_sort_pairs(R, R_dev, b.tile_buf[0], b.id_buf[0], b.tile_buf[1], b.id_buf[1], 0,
+                                   tile_sort_bits(ntiles), b.sort, false,
+                                   hist_passes > 0 ? SORT_HIST_DONE : SORT_FRESH, st, &fk, &fv);
         }
         if (rc) return rc;
         if (fv != b.point_list || fk != b.tile_sorted) {
@@ -366,7 +427,7 @@ extern "C" int bags_rasterize_forward(
     }
     {
         ProfScope ps(BAGS_STAGE_RANGES, st);
-        rc = launch_ranges(R, ntiles, b.tile_sorted, img.ranges, st);
+        rc = launch_ranges(R, R_dev, ntiles, b.tile_sorted, img.ranges, st);
     }
     if (rc) return rc;
     {
@@ -375,7 +436,40 @@ extern "C" int bags_rasterize_forward(
     }
     if (rc) return rc;
     if (debug) BAGS_CUDA_OK(cudaStreamSynchronize(st));
-    return R;
+    return async ? 0 : R;
+}
+
+extern "C" int bags_rasterize_forward(
+    bags_alloc_fn geom_alloc, void* geom_user, bags_alloc_fn binning_alloc, void* binning_user,
+    bags_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+    float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+    const float* projmatrix, const float* intrinsic, const float* cam_pos, const float* shift_factors, float tan_fovx,
+    float tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha, int* radii, float* mean2Dx,
+    float* mean2Dy, int debug, void* stream) {
+    (void)intrinsic;  // passed through by the reference too, never read by live code (forward.cu:352)
+    return forward_impl(geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, P, D, M,
+                        background, width, height, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+                        rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, shift_factors, tan_fovx, tan_fovy,
+                        prefiltered, out_color, out_depth, out_alpha, radii, mean2Dx, mean2Dy, debug, -1, nullptr,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int bags_rasterize_forward_async(
+    bags_alloc_fn geom_alloc, void* geom_user, bags_alloc_fn binning_alloc, void* binning_user,
+    bags_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+    float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+    const float* projmatrix, const float* intrinsic, const float* cam_pos, const float* shift_factors, float tan_fovx,
+    float tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha, int* radii, float* mean2Dx,
+    float* mean2Dy, int capacity, unsigned long long* num_rendered_out, void* stream) {
+    (void)intrinsic;
+    BAGS_REQUIRE(capacity >= 0, "negative capacity");
+    return forward_impl(geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, P, D, M,
+                        background, width, height, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+                        rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, shift_factors, tan_fovx, tan_fovy,
+                        prefiltered, out_color, out_depth, out_alpha, radii, mean2Dx, mean2Dy, 0, capacity,
+                        num_rendered_out, (cudaStream_t)stream);
 }
 
 extern "C" int bags_rasterize_backward_accum(
@@ -395,6 +489,15 @@ extern "C" int bags_rasterize_backward_accum(
     BAGS_REQUIRE(P >= 0 && R >= 0 && width > 0 && height > 0, "negative size");
     BAGS_REQUIRE(scratch && dL_dprojmatrix && dL_dviewmatrix && dL_dcampos && dL_dshift, "null pose output/scratch");
 
+    if (P == 0) {
+        // The reference launches nothing and returns .mean(0) of empty (0, k) tensors (rasterize_points.cu:274): NaN.
+        // (0xFF bytes are a quiet NaN.)
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dprojmatrix, 0xFF, 16 * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dviewmatrix, 0xFF, 16 * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dcampos, 0xFF, 3 * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dshift, 0xFF, 3 * sizeof(float), st));
+        return 0;
+    }
     char* sp = (char*)align_up((size_t)scratch);
     float* gacc = (float*)sp;
     double* pose_acc = (double*)(sp + align_up((size_t)P * GACC_STRIDE * sizeof(float)));

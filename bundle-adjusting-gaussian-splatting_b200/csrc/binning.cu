@@ -19,6 +19,8 @@
 #include "../../include/bags_b200.h"
 #include "common.cuh"
 
+#include <atomic>
+
 namespace bags {
 
 // =================================================================================================================
@@ -45,9 +47,21 @@ __device__ __forceinline__ void st_volatile_u32(u32* p, u32 v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Element count of a launch.  Synchronous callers know it on the host (n_dev == NULL: n_cap is the count).  The
+// asynchronous forward (bags_rasterize_forward_async) sizes its grids by the caller's capacity and every kernel reads the
+// actual count -- written by the preprocess kernel -- from device memory; a count above the capacity is clamped (the
+// caller sees the overflow in the count it gets back and must re-run with a larger capacity).
+__device__ __forceinline__ int resolve_n(const int n_cap, const unsigned long long* __restrict__ n_dev) {
+    if (n_dev == nullptr) return n_cap;
+    const unsigned long long v = *n_dev;
+    return v < (unsigned long long)n_cap ? (int)v : n_cap;
+}
+
 // Histograms of every digit position in one read of the keys.
 __global__ void __launch_bounds__(512)
-sort_hist_kernel(const u32* __restrict__ keys, int n, int begin_bit, int end_bit, u32* __restrict__ ghist) {
+sort_hist_kernel(const u32* __restrict__ keys, int n_cap, const unsigned long long* __restrict__ n_dev, int begin_bit,
+                 int end_bit, u32* __restrict__ ghist) {
+    const int n = resolve_n(n_cap, n_dev);
     __shared__ u32 sh[SORT_MAX_PASSES][RADIX];
     for (int i = threadIdx.x; i < SORT_MAX_PASSES * RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
@@ -192,8 +206,9 @@ __device__ __forceinline__ void rank_items(const u32 (&key)[ITEMS], u32 (&rank)[
 template <bool IOTA, int LOOKBACK, bool BYTE, int ITEMS, bool HWMATCH>
 __global__ void __launch_bounds__(SORT_THREADS, 4)
 onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, u32* __restrict__ keys_out,
-                     u32* __restrict__ vals_out, int n, int shift, int bits, const u32* __restrict__ ghist,
-                     u32* __restrict__ tile_counter, u32* __restrict__ status) {
+                     u32* __restrict__ vals_out, int n_cap, const unsigned long long* __restrict__ n_dev, int shift,
+                     int bits, const u32* __restrict__ ghist, u32* __restrict__ tile_counter,
+                     u32* __restrict__ status) {
     constexpr int TILE = ITEMS * SORT_THREADS;
     extern __shared__ u32 sort_smem[];
     u32* s_keys = sort_smem;                                             // [TILE] keys in locally sorted order
@@ -210,6 +225,10 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     __syncthreads();
     const u32 tile = s_tile;
     const long long tile_base = (long long)tile * TILE;
+    const int n = resolve_n(n_cap, n_dev);
+    // grids sized by a capacity: the CTAs that drew a tile past the end leave (tile ids are handed out in order, so
+    // no live tile ever looks back at one of them)
+    if (tile_base >= (long long)n) return;
     const int nvalid = (int)min((long long)TILE, (long long)n - tile_base);
     const bool full = nvalid == TILE;                               // CTA-uniform
     const u32 mask = (1u << bits) - 1u;
@@ -308,10 +327,20 @@ onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ va
     }
 }
 
+// Zeroes the bookkeeping of one sort (digit histograms, dynamic tile counters, look-back words).  Separate from
+// launch_sort_pairs so that a producer kernel can fill the digit histograms on the way (emit_fill does, for the tile
+// sort) between the two.
+int sort_prepare(SortScratch& sc, cudaStream_t st) {
+    BAGS_CUDA_OK(cudaMemsetAsync(sc.ghist, 0, sc.zero_bytes, st));
+    return 0;
+}
+
 // Sorts bits [begin_bit, end_bit).  Ping-pongs between (keys_in, vals_in) and (keys_out, vals_out); when the number
 // of passes is even the result lands in the *_in buffers, so the final location is reported through final_*.
-int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* vals_out, int begin_bit, int end_bit,
-                      SortScratch& sc, bool iota_vals, cudaStream_t st, u32** final_keys, u32** final_vals) {
+// n_dev: see resolve_n (NULL = n is exact).  hist_mode: SORT_FRESH / SORT_PREPARED / SORT_HIST_DONE (common.cuh).
+int launch_sort_pairs(int n, const unsigned long long* n_dev, u32* keys_in, u32* vals_in, u32* keys_out,
+                      u32* vals_out, int begin_bit, int end_bit, SortScratch& sc, bool iota_vals, int hist_mode,
+                      cudaStream_t st, u32** final_keys, u32** final_vals) {
     const int npass = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
     if (npass < 1 || npass > SORT_MAX_PASSES) {
         set_error("sort: unsupported bit range [%d,%d)", begin_bit, end_bit);
@@ -322,10 +351,15 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
         *final_vals = vals_in;
         return 0;
     }
-    BAGS_CUDA_OK(cudaMemsetAsync(sc.ghist, 0, sc.zero_bytes, st));
-    int hist_blocks = min((n + 512 * 8 - 1) / (512 * 8), 148 * 4);
-    sort_hist_kernel<<<hist_blocks, 512, 0, st>>>(keys_in, n, begin_bit, end_bit, sc.ghist);
-    BAGS_LAUNCH_OK("sort_hist_kernel");
+    if (hist_mode == SORT_FRESH) {
+        int rc = sort_prepare(sc, st);
+        if (rc) return rc;
+    }
+    if (hist_mode != SORT_HIST_DONE) {
+        int hist_blocks = min((n + 512 * 8 - 1) / (512 * 8), 148 * 4);
+        sort_hist_kernel<<<hist_blocks, 512, 0, st>>>(keys_in, n, n_dev, begin_bit, end_bit, sc.ghist);
+        BAGS_LAUNCH_OK("sort_hist_kernel");
+    }
     // Keys per CTA: 4096 when the pass runs in several waves (throughput bound), 2048 when even that leaves the GPU
     // under-filled -- a pass over 1 M keys is bounded by the latency of one CTA's instruction stream, which halves.
     const bool small = g_sort_small_tiles && (n + SORT_TILE - 1) / SORT_TILE < 2 * 148;
@@ -340,18 +374,19 @@ int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* val
         u32* status = sc.status + (size_t)p * sc.ntiles * RADIX;
         const bool iota = p == 0 && iota_vals;
         const bool byte_digit = bits == 8 && (sft & 7) == 0;
-        // the shared-memory attribute is per device and per kernel: set once for each
+        // the shared-memory attribute is per device and per kernel: set once for each (the flag is only a cache of
+        // an idempotent call, so concurrent first calls from two host threads are harmless)
 #define BAGS_PASS(IOTA, LB, BYTE, ITEMS, HWM)                                                                      \
     do {                                                                                                           \
-        static bool attr_set[64] = {};   /* per kernel variant (expansion site) and device */                      \
-        if (!attr_set[cur_dev & 63]) {                                                                             \
+        static std::atomic<unsigned char> attr_set[64];   /* per kernel variant (expansion site) and device */     \
+        if (!attr_set[cur_dev & 63].load(std::memory_order_acquire)) {                                             \
             BAGS_CUDA_OK(cudaFuncSetAttribute(onesweep_pass_kernel<IOTA, LB, BYTE, ITEMS, HWM>,                    \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
                                               (int)sort_smem_bytes(ITEMS)));                                       \
-            attr_set[cur_dev & 63] = true;                                                                         \
+            attr_set[cur_dev & 63].store(1, std::memory_order_release);                                            \
         }                                                                                                          \
         onesweep_pass_kernel<IOTA, LB, BYTE, ITEMS, HWM><<<ntiles, SORT_THREADS, sort_smem_bytes(ITEMS), st>>>(    \
-            ki, vi, ko, vo, n, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status);                      \
+            ki, vi, ko, vo, n, n_dev, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status);               \
     } while (0)
 #define BAGS_PASS_I(IOTA, LB, BYTE)                                                                                \
     do {                                                                                                           \
@@ -462,13 +497,22 @@ constexpr int EMIT_FILL_WINDOW = EMIT_FILL_SLOTS + 1;                  // staged
                                                                        // every Gaussian has >= 1 tile)
 constexpr int EMIT_FILL_PAD = 2 * EMIT_FILL_SLOTS;                     // power-of-two search array (sentinel padded)
 
+// `ghist` (may be NULL): the digit histograms of the tile sort ([pass][RADIX], 8-bit digits of the tile id from bit 0,
+// `hist_passes` of them) are accumulated here, where the tile ids are produced, instead of by a separate read of the
+// R keys (sort_hist_kernel).
 __global__ void __launch_bounds__(EMIT_FILL_THREADS)
-emit_fill_kernel(int P, u32 R, const u32* __restrict__ offsets, const u32* __restrict__ sorted_idx,
-                 const ushort4* __restrict__ rect, int grid_x, u32* __restrict__ tile_out, u32* __restrict__ id_out) {
+emit_fill_kernel(int P, int R_cap, const unsigned long long* __restrict__ R_dev, const u32* __restrict__ offsets,
+                 const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect, int grid_x,
+                 u32* __restrict__ tile_out, u32* __restrict__ id_out, u32* __restrict__ ghist, int hist_passes) {
     __shared__ u32 s_off[EMIT_FILL_PAD];
+    __shared__ u32 s_hist[2][RADIX];
     __shared__ int s_lo;
     const int tid = threadIdx.x, lane = tid & 31;
     const u32 slot0 = blockIdx.x * (u32)EMIT_FILL_SLOTS;
+    const u32 R = (u32)resolve_n(R_cap, R_dev);
+    if (slot0 >= R) return;   // CTA-uniform (grid sized by the capacity)
+    if (ghist != nullptr)
+        for (int k = tid; k < 2 * RADIX; k += EMIT_FILL_THREADS) (&s_hist[0][0])[k] = 0;
 
     // first Gaussian (in depth order) of this CTA's range: the last i with offsets[i] <= slot0
     if (tid < 32) {
@@ -532,8 +576,20 @@ emit_fill_kernel(int P, u32 R, const u32* __restrict__ offsets, const u32* __res
         const u32 w = max((u32)r[it].z, 1u);
         const u32 ty = (u32)r[it].y + local / w;
         const u32 tx = (u32)r[it].x + local % w;
-        tile_out[slot[it]] = ty * (u32)grid_x + tx;
+        const u32 tile = ty * (u32)grid_x + tx;
+        tile_out[slot[it]] = tile;
         id_out[slot[it]] = g[it];
+        if (ghist != nullptr) {
+            atomicAdd(&s_hist[0][tile & (RADIX - 1)], 1u);
+            if (hist_passes > 1) atomicAdd(&s_hist[1][(tile >> RADIX_BITS) & (RADIX - 1)], 1u);
+        }
+    }
+    if (ghist != nullptr) {
+        __syncthreads();
+        for (int k = tid; k < hist_passes * RADIX; k += EMIT_FILL_THREADS) {
+            const u32 v = (&s_hist[0][0])[k];
+            if (v) atomicAdd(&ghist[k], v);
+        }
     }
 }
 
@@ -546,11 +602,14 @@ int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offs
     return 0;
 }
 
-int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, const u32* offsets, BinningState& b,
-                     int grid_x, cudaStream_t st) {
+// hist_passes: 1 or 2 -> the tile sort's digit histograms are accumulated into b.sort.ghist (sort_prepare() must have
+// run); 0 -> not (more than two 8-bit digits: the sort makes its own histogram pass).
+int launch_emit_fill(int P, int R, const unsigned long long* R_dev, const GeomState& g, const u32* sorted_idx,
+                     const u32* offsets, BinningState& b, int grid_x, int hist_passes, cudaStream_t st) {
     const int blocks = (R + EMIT_FILL_SLOTS - 1) / EMIT_FILL_SLOTS;
-    emit_fill_kernel<<<blocks, EMIT_FILL_THREADS, 0, st>>>(P, (u32)R, offsets, sorted_idx, g.rect, grid_x,
-                                                          b.tile_buf[0], b.id_buf[0]);
+    emit_fill_kernel<<<blocks, EMIT_FILL_THREADS, 0, st>>>(P, R, R_dev, offsets, sorted_idx, g.rect, grid_x,
+                                                          b.tile_buf[0], b.id_buf[0],
+                                                          hist_passes > 0 ? b.sort.ghist : nullptr, hist_passes);
     BAGS_LAUNCH_OK("emit_fill_kernel");
     return 0;
 }
@@ -561,7 +620,9 @@ int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, co
 // =================================================================================================================
 constexpr int RANGE_ITEMS = 4;
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(int R, const u32* __restrict__ tile_sorted, uint2* __restrict__ ranges) {
+tile_ranges_kernel(int R_cap, const unsigned long long* __restrict__ R_dev, const u32* __restrict__ tile_sorted,
+                   uint2* __restrict__ ranges) {
+    const int R = resolve_n(R_cap, R_dev);
     // thread-striped over RANGE_ITEMS * 256 consecutive elements per CTA (coalesced loads)
     const int base = blockIdx.x * (256 * RANGE_ITEMS) + threadIdx.x;
 #pragma unroll
@@ -582,10 +643,12 @@ tile_ranges_kernel(int R, const u32* __restrict__ tile_sorted, uint2* __restrict
     }
 }
 
-int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st) {
+int launch_ranges(int R, const unsigned long long* R_dev, int ntiles, const u32* tile_sorted, uint2* ranges,
+                  cudaStream_t st) {
     BAGS_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)ntiles * sizeof(uint2), st));
     if (R > 0) {
-        tile_ranges_kernel<<<(R + 256 * RANGE_ITEMS - 1) / (256 * RANGE_ITEMS), 256, 0, st>>>(R, tile_sorted, ranges);
+        tile_ranges_kernel<<<(R + 256 * RANGE_ITEMS - 1) / (256 * RANGE_ITEMS), 256, 0, st>>>(R, R_dev, tile_sorted,
+                                                                                            ranges);
         BAGS_LAUNCH_OK("tile_ranges_kernel");
     }
     return 0;
@@ -628,7 +691,8 @@ extern "C" int bags_sort_pairs_u32(int n, uint32_t* keys_in, uint32_t* vals_in, 
     SortScratch sc = SortScratch::from(p, n);
     u32 *fk, *fv;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_sort_pairs(n, keys_in, vals_in, keys_out, vals_out, begin_bit, end_bit, sc, false, st, &fk, &fv);
+    int rc = launch_sort_pairs(n, nullptr, keys_in, vals_in, keys_out, vals_out, begin_bit, end_bit, sc, false,
+                               SORT_FRESH, st, &fk, &fv);
     if (rc) return rc;
     if (n > 0 && fk != keys_out) {
         BAGS_CUDA_OK(cudaMemcpyAsync(keys_out, fk, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));

@@ -166,16 +166,24 @@ int launch_preprocess_fwd(const FwdArgs& a, GeomState& g, int* radii, float* mea
 int launch_unpack(int P, int R, int W, int H, const GeomState& g, const BinningState& b, const ImageState& img,
                   u32* tiles_touched, u32* depth_bits, float* xy, float* conic_opacity, float* rgb, u32* point_list,
                   u64* point_list_keys, u32* ranges, u32* n_contrib, float* final_T, cudaStream_t st);
-int launch_sort_pairs(int n, u32* keys_in, u32* vals_in, u32* keys_out, u32* vals_out, int begin_bit, int end_bit,
-                      SortScratch& sc, bool iota_vals, cudaStream_t st, u32** final_keys, u32** final_vals);
+// n_dev / R_dev: device location of the element count when the host only knows a capacity (NULL: the count is exact)
+// hist_mode of launch_sort_pairs: SORT_FRESH zeroes the bookkeeping and counts the digits itself; SORT_PREPARED: the
+// caller has zeroed the bookkeeping (sort_prepare, or as part of a larger memset); SORT_HIST_DONE: ... and a producer
+// kernel has already filled the digit histograms of keys_in (no histogram launch).
+enum { SORT_FRESH = 0, SORT_PREPARED = 1, SORT_HIST_DONE = 2 };
+int sort_prepare(SortScratch& sc, cudaStream_t st);
+int launch_sort_pairs(int n, const unsigned long long* n_dev, u32* keys_in, u32* vals_in, u32* keys_out,
+                      u32* vals_out, int begin_bit, int end_bit, SortScratch& sc, bool iota_vals, int hist_mode,
+                      cudaStream_t st, u32** final_keys, u32** final_vals);
 int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st);
-int launch_emit_fill(int P, int R, const GeomState& g, const u32* sorted_idx, const u32* offsets, BinningState& b,
-                     int grid_x, cudaStream_t st);
+int launch_emit_fill(int P, int R, const unsigned long long* R_dev, const GeomState& g, const u32* sorted_idx,
+                     const u32* offsets, BinningState& b, int grid_x, int hist_passes, cudaStream_t st);
 int set_sort_lookback(int value);
 int set_sort_small_tiles(int value);
 int set_sort_hwmatch(int value);
 int set_pbwd_min_blocks(int value);
-int launch_ranges(int R, int ntiles, const u32* tile_sorted, uint2* ranges, cudaStream_t st);
+int launch_ranges(int R, const unsigned long long* R_dev, int ntiles, const u32* tile_sorted, uint2* ranges,
+                  cudaStream_t st);
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
 int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, const ImageState& img, const float* bg,

@@ -277,7 +277,7 @@ extern "C" int bags_knn_mean_dist2(int P, const float* points, float* mean_dist2
     knn_morton_kernel<<<pb, KNN_THREADS, 0, st>>>(P, points, s.bbox, s.code_a);
     BAGS_LAUNCH_OK("knn_morton_kernel");
     u32 *fk, *order;
-    int rc = launch_sort_pairs(P, s.code_a, s.idx_a, s.code_b, s.idx_b, 0, 30, s.sort, true, st, &fk, &order);
+    int rc = launch_sort_pairs(P, nullptr, s.code_a, s.idx_a, s.code_b, s.idx_b, 0, 30, s.sort, true, SORT_FRESH, st, &fk, &order);
     if (rc) return rc;
     knn_gather_kernel<<<pb, KNN_THREADS, 0, st>>>(P, points, order, s.pts, s.l0);
     BAGS_LAUNCH_OK("knn_gather_kernel");

@@ -13,14 +13,25 @@ pupil-shift gradients that ``--opt_cam`` and ``--opt_intrinsic`` consume (refere
 ``gaussian_renderer/__init__.py:render()`` of the reference runs on top of this unchanged.
 
 The native work happens in ``libbags_b200.so`` (hand-written sm_100a kernels, C ABI in include/bags_b200.h)
-reached through ``_C``; there is no CPU path.
+reached through ``_C``, a compiled PyTorch C++ extension with the reference's four pybind symbols
+(3dgs-pose/ext.cpp:15-20; source: csrc/ext.cpp); there is no CPU path.
+
+Extensions beyond the reference API (all off unless asked for): gradient sinks (``register_grad_sink`` +
+``grad_sinks()``), the asynchronous forward (``AsyncForward``).
 """
+import contextlib
 from typing import NamedTuple
 
 import torch
 import torch.nn as nn
 
-from . import _C
+try:
+    from . import _C
+except ImportError as _e:       # no fallback: the extension is the product
+    raise ImportError(
+        "bags_b200: the compiled extension diff_gaussian_rasterization._C is missing or does not load (" + str(_e) +
+        "); build it with `python bundle-adjusting-gaussian-splatting_b200/build.py` -- there is no CPU or PyTorch "
+        "fallback for the rasterizer") from _e
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -44,17 +55,25 @@ class GaussianRasterizationSettings(NamedTuple):
     debug_iter: int
 
 
-# ---- gradient sinks (extension; off unless a caller registers one) ------------------------------------------------
+# ---- gradient sinks (extension; off unless a caller registers one AND activates them) ------------------------------
 # The reference returns fresh gradient tensors and autograd then runs `param.grad += fresh` for each of the five
 # Gaussian parameters: three more passes over 236 B/Gaussian per view.  A caller that accumulates over views (gradient
 # accumulation, the view-parallel step of bags_view_parallel.py) can register the buffer a leaf's gradient is summed
 # into; the backward kernel then adds into that buffer directly and this input's autograd slot returns None.
+#
+# Because a sink changes what `backward` does to a leaf (its `.grad` buffer is written by the kernel, tensor hooks and
+# DDP hooks on the leaf do not fire, `torch.autograd.grad(...)` w.r.t. the leaf gets None), registered sinks are only
+# consulted while they are ACTIVE: inside `with grad_sinks():` around the training forward+backward, or after
+# `set_grad_sinks_active(True)`.  Evaluation renders, gradient probes and double-backward checks outside that scope see
+# the reference's behaviour.
 _GRAD_SINKS = {}        # (device index, data_ptr) -> (weakref to the leaf, buffer)
+_SINKS_ACTIVE = False
 
 
 def register_grad_sink(param, buffer):
     """Accumulate the rasterizer's gradient w.r.t. `param` (a leaf passed as means3D / shs / opacities / scales /
-    rotations) directly into `buffer` (same shape, fp32, contiguous, same device).  Typically buffer is param.grad."""
+    rotations) directly into `buffer` (same shape, fp32, contiguous, same device) whenever sinks are active (see
+    `grad_sinks`).  Typically buffer is param.grad."""
     import weakref
     if not (param.is_cuda and buffer.is_cuda and param.device == buffer.device):
         raise RuntimeError("bags_b200: gradient sinks need CUDA tensors on one device (there is no CPU path)")
@@ -67,8 +86,25 @@ def unregister_grad_sink(param):
     _GRAD_SINKS.pop((param.device.index, param.data_ptr()), None)
 
 
+def set_grad_sinks_active(active):
+    """Process-wide switch for the registered sinks; returns the previous state."""
+    global _SINKS_ACTIVE
+    prev, _SINKS_ACTIVE = _SINKS_ACTIVE, bool(active)
+    return prev
+
+
+@contextlib.contextmanager
+def grad_sinks(active=True):
+    """`with grad_sinks():` -- forwards issued inside use the registered gradient sinks in their backward."""
+    prev = set_grad_sinks_active(active)
+    try:
+        yield
+    finally:
+        set_grad_sinks_active(prev)
+
+
 def _sink_of(t):
-    if not _GRAD_SINKS or t is None or not t.is_cuda or t.numel() == 0 or not t.requires_grad:
+    if t is None or not t.is_cuda or t.numel() == 0 or not t.requires_grad:
         return None
     ent = _GRAD_SINKS.get((t.device.index, t.data_ptr()))
     if ent is None:
@@ -80,10 +116,65 @@ def _sink_of(t):
     return buf
 
 
+# ---- asynchronous forward (extension) -----------------------------------------------------------------------------
+class AsyncForward:
+    """Forward passes issued inside `with AsyncForward(capacity) as af:` never wait for the GPU
+    (bags_rasterize_forward_async): the binning buffer and the binning grids are sized by `capacity` tile instances
+    instead of by a num_rendered the host has to read back (the reference blocks on that copy in every forward,
+    rasterizer_impl.cu:291).  The whole view -- forward, loss, backward -- becomes a pure enqueue, so the host can run
+    ahead of the GPU by any number of views and the sequence can be captured in a CUDA graph.
+
+    The actual count of every forward lands, in stream order, in `af.counts` (pinned int64[slots], slot k % slots for
+    the k-th forward of the scope, -1 = not written yet).  A count above the capacity means that view's tile lists
+    were truncated and its image and gradients are wrong: call `af.check()` (after a synchronisation point of your
+    choice -- e.g. where the loss is read back, one step late) to raise on that, and re-run with a larger capacity.
+    `suggested_capacity()` gives 1.25 x the largest count seen + 64 Ki."""
+
+    _current = None
+
+    def __init__(self, capacity, slots=64, device=None):
+        self.capacity = int(capacity)
+        if self.capacity < 0 or self.capacity >= (1 << 30):
+            raise ValueError("capacity must be in [0, 2^30)")
+        self.slots = int(slots)
+        self.counts = torch.full((self.slots,), -1, dtype=torch.int64).pin_memory()
+        self._k = 0
+        self._prev = None
+        self.max_seen = 0
+
+    def __enter__(self):
+        self._prev, AsyncForward._current = AsyncForward._current, self
+        return self
+
+    def __exit__(self, *exc):
+        AsyncForward._current = self._prev
+        return False
+
+    def _next_slot(self):
+        s = self.counts[self._k % self.slots:self._k % self.slots + 1]
+        self._k += 1
+        return s
+
+    def check(self):
+        """Raises if any finished forward of this scope overflowed its capacity.  Only looks at host memory: call it
+        after the stream (or an event behind the forwards of interest) has been synchronised."""
+        m = int(self.counts.max())
+        self.max_seen = max(self.max_seen, m)
+        if m > self.capacity:
+            raise RuntimeError(f"bags_b200: asynchronous forward overflowed its binning capacity ({m} tile instances > "
+                               f"capacity {self.capacity}); the images / gradients of that view are truncated -- "
+                               f"re-run with capacity >= {self.suggested_capacity()}")
+        return m
+
+    def suggested_capacity(self):
+        m = max(self.max_seen, int(self.counts.max()))
+        return int(m * 1.25) + (64 << 10)
+
+
 def rasterize_gaussians(means3D, means2D, means2D_densify, shift_factors, sh, colors_precomp, opacities, scales,
                         rotations, cov3Ds_precomp, raster_settings):
     sinks = None
-    if _GRAD_SINKS and torch.is_grad_enabled():
+    if _SINKS_ACTIVE and _GRAD_SINKS and torch.is_grad_enabled():
         sinks = {k: b for k, b in (("means3D", _sink_of(means3D)), ("sh", _sink_of(sh)),
                                    ("opacity", _sink_of(opacities)), ("scales", _sink_of(scales)),
                                    ("rotations", _sink_of(rotations))) if b is not None} or None
@@ -101,7 +192,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (rs.bg, means3D, shift_factors, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
                 cov3Ds_precomp, world_view, full_proj, rs.intrinsic, rs.tanfovx, rs.tanfovy, rs.image_height,
                 rs.image_width, sh, rs.sh_degree, camera_center, rs.prefiltered, rs.debug)
-        if rs.debug:
+        af = AsyncForward._current
+        if af is not None:
+            out = _C.rasterize_gaussians_async(*args[:-1], af.capacity, af._next_slot())
+        elif rs.debug:
             # (the reference's debug branch unpacks the wrong tuple arity and cannot run; this one works)
             cpu_args = cpu_deep_copy_tuple(args)
             try:
@@ -142,16 +236,18 @@ class _RasterizeGaussians(torch.autograd.Function):
                 ctx.world_view, ctx.full_proj, rs.intrinsic, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width,
                 grad_out_color, grad_out_depth, grad_out_weight, sh, rs.sh_degree, ctx.camera_center, geomBuffer,
                 ctx.num_rendered, binningBuffer, imgBuffer, weights, rs.debug)
+        sk = ctx.grad_sinks or {}
+        sinks = (sk.get("means3D"), sk.get("sh"), sk.get("opacity"), sk.get("scales"), sk.get("rotations"))
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
-                out = _C.rasterize_gaussians_backward(*args, sinks=ctx.grad_sinks)
+                out = _C.rasterize_gaussians_backward(*args, *sinks)
             except Exception:
                 torch.save(cpu_args, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise
         else:
-            out = _C.rasterize_gaussians_backward(*args, sinks=ctx.grad_sinks)
+            out = _C.rasterize_gaussians_backward(*args, *sinks)
         (grad_means2D, grad_means2D_densify, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp,
          grad_sh, grad_scales, grad_rotations, grad_camera_center, grad_full_proj, grad_world_view,
          grad_shift_factors, covariance) = out

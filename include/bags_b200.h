@@ -18,6 +18,8 @@
  *                                    that --outside_rasterizer runs on every rendered canvas
  *   bags_loss_forward/backward    <- utils/loss_utils.py:18-19 (l1_loss) and :49-76 (ssim / _ssim: five grouped 11x11
  *                                    Gaussian convolutions + the SSIM map), combined at train.py:325
+ *   bags_rasterize_forward_async  <- the same forward without the blocking read-back of num_rendered
+ *                                    (rasterizer_impl.cu:291): caller-provided binning capacity, count kept on the device
  *   bags_unpack_state             (test-only) exposes the private binning/image state so parity tests can compare
  *                                  tiles_touched / sorted keys / point list / ranges / n_contrib / final_T bit for bit
  *                                  with the reference's GeometryState/BinningState/ImageState (rasterizer_impl.h:21-72).
@@ -25,6 +27,11 @@
  * All matrices use the reference's convention: 16 floats, flat index m[4*c + r] (the transposed, row-vector form that
  * scene/cameras.py hands to GaussianRasterizationSettings).  All tensors are fp32 and contiguous unless stated.
  * Return value: >= 0 on success, a negative BAGS_E_* code on failure (bags_last_error() gives the text).
+ *
+ * Threading: every entry point may be called concurrently from several host threads (any devices, any streams); the
+ * library keeps no per-call state outside the caller's buffers (the pinned word + event a synchronous forward needs
+ * come from a locked pool).  bags_last_error() is per thread.  The tuning knobs and the profiling switch are process
+ * wide and meant to be set while nothing else runs.
  */
 #ifndef BAGS_B200_H_INCLUDED
 #define BAGS_B200_H_INCLUDED
@@ -88,6 +95,51 @@ int bags_rasterize_forward(
     float* mean2Dx,
     float* mean2Dy,
     int debug,
+    void* stream);
+
+/* Asynchronous forward (extension; the reference blocks on a 4-byte device-to-host copy of num_rendered in every
+ * forward, rasterizer_impl.cu:291, to size its binning buffer).  Same contract as bags_rasterize_forward except:
+ *   - nothing waits on the device and no host memory is allocated: the call only enqueues work on `stream`, so it can be
+ *     captured in a CUDA graph and the host can run any number of views ahead of the GPU;
+ *   - `capacity` is the number of tile instances the binning buffer is sized for (binning_alloc is asked for
+ *     bags_binning_bytes(P, capacity, ...) bytes; pass the same number as `R` to the backward).  The grids of the emit /
+ *     tile-sort / range kernels are sized by it and the kernels read the actual count on the device;
+ *   - *num_rendered_out (device or pinned host memory, may be NULL) receives the actual count, in stream order.
+ *     A count above `capacity` means the tile lists were truncated: the images and every gradient of that view are
+ *     WRONG (nothing is written out of bounds) and the caller must re-render with a larger capacity.  A trainer checks
+ *     the count together with the loss, one step late; the count of the previous iteration plus some slack is the
+ *     natural capacity.
+ * Returns 0 on success. */
+int bags_rasterize_forward_async(
+    bags_alloc_fn geom_alloc, void* geom_user,
+    bags_alloc_fn binning_alloc, void* binning_user,
+    bags_alloc_fn image_alloc, void* image_user,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* intrinsic,
+    const float* cam_pos,
+    const float* shift_factors,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_depth,
+    float* out_alpha,
+    int* radii,
+    float* mean2Dx,
+    float* mean2Dy,
+    int capacity,
+    unsigned long long* num_rendered_out,
     void* stream);
 
 /* Backward.  Dense per-Gaussian outputs ([P,...], every row written, zero for culled Gaussians):

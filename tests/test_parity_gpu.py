@@ -428,6 +428,7 @@ def test_gradient_sinks_equal_autograd_accumulation(sh_degree):
         pose, m2d_grads, radii_all = [], [], []
         shift = torch.zeros(3, device=d, requires_grad=True)
         try:
+          with params.accumulating():       # the registered sinks are only consulted inside this scope
             for cam, up in zip(cams, ups):
                 view = cam.viewmatrix.to(d).requires_grad_(True)
                 proj = cam.projmatrix.to(d).requires_grad_(True)
@@ -509,6 +510,7 @@ def test_view_streams_pipeline_equals_serial(sinks):
         pipe = VP.ViewStreams(d, depth=depth)
         images, pose = [], []
         try:
+          with params.accumulating():
             for rep in range(2):        # twice: the second round reuses streams, events and cached blocks
                 params.zero_grad()
                 images, leaves = [], []

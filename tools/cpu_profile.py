@@ -34,6 +34,7 @@ def main():
     params = VP.FlatGaussianParams(gs.means3D.to(dev), gs.shs.to(dev), gs.opacities.to(dev), gs.scales.to(dev),
                                    gs.rotations.to(dev), device=dev)
     params.enable_direct_accumulation(dgr)
+    dgr.set_grad_sinks_active(True)
     bg = torch.zeros(3, device=dev)
     shift = torch.zeros(3, device=dev, requires_grad=True)
     vm, pm, cp = [t.to(dev).requires_grad_(True) for t in (cam.viewmatrix, cam.projmatrix, cam.campos)]

@@ -12,6 +12,8 @@ import parity_common as pc  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.004
+impl = sys.argv[3] if len(sys.argv) > 3 else "ours"       # "ref": the unmodified reference build (oracle/_ref)
+mod = pc.load_ref() if impl == "ref" else pc.load_ours()
 c = S.CONFIGS["C3"]
 cam0 = S.make_camera(c["W"], c["H"], seed=100)
 gs = S.make_gaussians(c["P"], cam0, scale=scale)
@@ -22,7 +24,7 @@ for phase in ("warm", "profiled"):
         torch.cuda.profiler.start()
     for v in range(n):
         cam = S.make_camera(c["W"], c["H"], seed=100 + v)
-        o = pc.run_view(pc.load_ours(), cam, gs, S.make_upstream(c["H"], c["W"], seed=1 + v), torch.device("cuda:0"))
+        o = pc.run_view(mod, cam, gs, S.make_upstream(c["H"], c["W"], seed=1 + v), torch.device("cuda:0"))
         print(phase, "view", v, "R", o["num_rendered"])
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
