@@ -197,10 +197,19 @@ __global__ void unpack_geom_kernel(int P, const float4* __restrict__ rec, const 
     if (rgb) { rgb[3 * i] = q2.x; rgb[3 * i + 1] = q2.y; rgb[3 * i + 2] = q2.z; }
 }
 
-__global__ void unpack_binning_kernel(int R, const u32* __restrict__ point_list, const u32* __restrict__ tile_sorted,
+// R_cap slots; only the first min(R_cap, *count) hold instances (asynchronous forward: R_cap is the caller's capacity)
+__global__ void unpack_binning_kernel(int R_cap, const unsigned long long* __restrict__ count,
+                                      const u32* __restrict__ point_list, const u32* __restrict__ tile_sorted,
                                       const float4* __restrict__ rec, u32* out_list, u64* out_keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
+    const unsigned long long c = *count;
+    const int R = c < (unsigned long long)R_cap ? (int)c : R_cap;
+    if (i >= R_cap) return;
+    if (i >= R) {
+        if (out_list) out_list[i] = 0u;
+        if (out_keys) out_keys[i] = 0ull;
+        return;
+    }
     u32 id = point_list[i];
     if (out_list) out_list[i] = id;
     if (out_keys) out_keys[i] = ((u64)tile_sorted[i] << 32) | (u64)__float_as_uint(rec[3 * (size_t)id].z);
@@ -215,8 +224,8 @@ int launch_unpack(int P, int R, int W, int H, const GeomState& g, const BinningS
         BAGS_LAUNCH_OK("unpack_geom_kernel");
     }
     if (R > 0 && (point_list || point_list_keys)) {
-        unpack_binning_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, b.point_list, b.tile_sorted, g.rec, point_list,
-                                                               point_list_keys);
+        unpack_binning_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, g.counters, b.point_list, b.tile_sorted, g.rec,
+                                                               point_list, point_list_keys);
         BAGS_LAUNCH_OK("unpack_binning_kernel");
     }
     size_t N = (size_t)W * H, T = (size_t)tiles_x(W) * tiles_y(H);

@@ -16,13 +16,17 @@
 //     those of the reference;
 //   * the backward only walks list positions below the largest n_contrib of the CTA / warp / patch.  The 13
 //     per-splat gradient terms of a thread's PPT pixels are added in registers, then reduced across the warp with
-//     ONE transposed butterfly per (warp, splat) (16 shuffles for 32 * PPT pixels) and committed with three 128-bit
-//     vector reductions (red.global.add.v4.f32) + one scalar into a packed 16-float record -- instead of 13 scalar
-//     global atomics per (pixel, splat) pair (backward.cu:1067-1116).  (Shared-memory fp32 atomics are CAS loops on
-//     this architecture, so a per-CTA shared accumulation stage was measured and dropped.)
-//   * the back-to-front recurrences accum = last_alpha * last_colour + (1 - last_alpha) * accum (backward.cu:1060,
-//     1069,1077) are evaluated at the end of the iteration that produces (alpha, colour) instead of at the start of
-//     the next one: same operands, same operations, five fewer live registers per pixel.
+//     ONE transposed butterfly per (warp, splat) (13 shuffles for 12 slots of 32 * PPT pixels) and committed with one
+//     predicated red.global.add.f32 (13 lanes, 13 consecutive words of a packed 16-float record) -- instead of 13
+//     scalar global atomics per (pixel, splat) pair (backward.cu:1067-1116).  (Shared-memory fp32 atomics are CAS
+//     loops on this architecture, so a per-CTA shared accumulation stage was measured and dropped.)
+//   * instruction count per contributing (pixel, splat) pair (round 2; the kernel is FP32-issue bound):
+//       - the five back-to-front "colour behind" recurrences (backward.cu:1060,1069,1077) are replaced by ONE scalar
+//         recurrence over sum_ch c_ch dL_dchannel (see the kernel);
+//       - the per-splat constants (opacity, 0.5 W, 0.5 H, -0.5, conic.x + conic.z) are factored out of the pixel
+//         loop: the record holds raw moments (sum q u, sum |q u|, sum q dx^2, ..., the contributing-pixel count) and
+//         preprocess_bwd.cu applies the constants once per Gaussian;
+//     same mathematical result, different fp32 rounding: covered by the 1e-4 relative-L2 gradient bar.
 #include "../../include/bags_b200.h"
 #include "common.cuh"
 
@@ -286,23 +290,36 @@ __device__ __forceinline__ void bfly(const float (&in)[N], float (&out)[N / 2], 
     }
 }
 
-// Warp sum of the 16 slots of `v`, added into the 16-float record `dst` (slots 0..12 are used; 13..15 are zero
-// padding and never written).  16 + 3 shuffles; lane 2k ends up with slot k.
-__device__ __forceinline__ void warp_reduce_commit(float (&v)[16], const int lane, float* dst) {
-    float a8[8], a4[4], a2[2], a1[1];
-    bfly<16, 16>(v, a8, lane);
-    bfly<8, 8>(a8, a4, lane);
-    bfly<4, 4>(a4, a2, lane);
-    bfly<2, 2>(a2, a1, lane);
-    float r0 = a1[0];
-    r0 += __shfl_xor_sync(FULL, r0, 1);
-    const float r1 = __shfl_down_sync(FULL, r0, 2);
-    const float r2 = __shfl_down_sync(FULL, r0, 4);
-    const float r3 = __shfl_down_sync(FULL, r0, 6);
-    if (!(lane & 7)) {
-        if (lane < 24) atomicAdd(reinterpret_cast<float4*>(dst + (lane >> 1)), make_float4(r0, r1, r2, r3));
-        else atomicAdd(dst + GA_COV, r0);
+// Warp sum of the 12 gradient slots of `v`, added into the splat's 16-float record `dst`, plus the number of
+// contributing pixels `cnt` (warp-uniform, from the validity ballots) into slot GA_COV.
+// Transposed butterfly 12 -> 6 -> 3 -> {2,1} -> 1 -> 1: 13 shuffles (a plain butterfly per slot would be 60).  Lane
+// (b16 b8 b4 b2 b1) ends up with slot 6*b16 + 3*b8 + (b4 ? 2 : b2); the 12 lanes with b1 == 0 that hold distinct slots
+// and one spare lane (the count) commit with ONE predicated red.global.add.f32: 13 consecutive words of one 64-byte
+// record.
+__device__ __forceinline__ void warp_reduce_commit12(const float (&v)[12], const float cnt, const int lane,
+                                                     float* dst) {
+    float a6[6], a3[3];
+    bfly<12, 16>(v, a6, lane);
+    bfly<6, 8>(a6, a3, lane);
+    const bool up4 = lane & 4, up2 = lane & 2;
+    // 3 -> lower lanes keep {0, 1}, upper lanes keep {2}
+    const float r0 = __shfl_xor_sync(FULL, up4 ? a3[0] : a3[2], 4);
+    const float r1 = __shfl_xor_sync(FULL, up4 ? a3[1] : 0.0f, 4);
+    const float b0 = (up4 ? a3[2] : a3[0]) + r0;
+    const float b1 = a3[1] + r1;                      // meaningful in the lower lanes only
+    // lower lanes: {0, 1} -> one each; upper lanes: plain add of their single slot
+    const float send = up4 ? b0 : (up2 ? b0 : b1);
+    const float keep = up4 ? b0 : (up2 ? b1 : b0);
+    float c = keep + __shfl_xor_sync(FULL, send, 2);
+    c += __shfl_xor_sync(FULL, c, 1);
+    int slot = ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + (up4 ? 2 : (up2 ? 1 : 0));
+    bool commit = !(lane & 1) && !(up4 && up2);
+    if (lane == 6) {                                  // (b4, b2) = (1, 1): a duplicate of lane 4's slot -> carries the count
+        slot = GA_COV;
+        c = cnt;
+        commit = true;
     }
+    if (commit) atomicAdd(dst + slot, c);
 }
 
 #ifdef BAGS_STATS
@@ -343,7 +360,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     __shared__ __align__(8) float2 sm_w[G_IN_SMEM ? 256 : 1];    // {dL_dweight, -T_final * (bg . dL_dcolour)}
     const u32 s_g = smem_addr(sm_g), s_w = smem_addr(sm_w);
     const float pyf0 = (float)(blockIdx.y * TILE_Y + wp.ly(lane, 0));   // row of pixel k is pyf0 + 4k (exact)
-    float T[PPT], ar0[PPT], ar1[PPT], ar2[PPT], ad[PPT], aa[PPT];
+    float T[PPT], Dacc[PPT];
     float g0[G_IN_SMEM ? 1 : PPT], g1[G_IN_SMEM ? 1 : PPT], g2[G_IN_SMEM ? 1 : PPT], gd[G_IN_SMEM ? 1 : PPT],
         gw[G_IN_SMEM ? 1 : PPT], nTbg[G_IN_SMEM ? 1 : PPT];
     u32 last_contributor[PPT], pmax[PPT];
@@ -376,15 +393,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
         } else {
             g0[k] = g.x; g1[k] = g.y; g2[k] = g.z; gd[k] = g.w; gw[k] = w; nTbg[k] = ntb;
         }
-        ar0[k] = ar1[k] = ar2[k] = ad[k] = aa[k] = 0.f;
+        Dacc[k] = 0.f;
         // Only list positions below the largest n_contrib of the patch / warp / CTA can contribute.
         pmax[k] = __reduce_max_sync(FULL, last_contributor[k]);
         warp_max = max(warp_max, pmax[k]);
     }
     const u32 warp_cells = wp.cells();
-
-    const float ddelx_dx = 0.5 * W;
-    const float ddely_dy = 0.5 * H;
 
     if (lane == 0) s_wmax[warp] = warp_max;
     __syncthreads();
@@ -419,21 +433,23 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                 const float dx = q0.x - pxf;
                 const float adx = __fmul_rn(dx, con_o.x), bdx = __fmul_rn(dx, con_o.y);
 
-                float v[16];
+                float v[12];
 #pragma unroll
-                for (int s = 0; s < 16; s++) v[s] = 0.f;
-                bool any_valid = false;
+                for (int s = 0; s < 12; s++) v[s] = 0.f;
+                u32 nvalid = 0;                      // contributing pixels of this warp (warp-uniform)
 #pragma unroll
                 for (int k = 0; k < PPT; k++) {
                     // warp-uniform: does the splat's box reach this patch, and is the position still live there?
                     if (((cm >> wp.cell_shift(k)) & 0x33u) == 0u || pos >= pmax[k]) continue;
-                    const float2 d = {dx, q0.y - (pyf0 + (float)(4 * k))};
-                    const float power = splat_power(dx, adx, bdx, d.y, con_o.z);
+                    const float dy = q0.y - (pyf0 + (float)(4 * k));
+                    const float power = splat_power(dx, adx, bdx, dy, con_o.z);
                     const float Gv = exp(power);
                     const float alpha = min(0.99f, con_o.w * Gv);
                     const bool valid = (pos < last_contributor[k]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    const u32 vmask = __ballot_sync(FULL, valid);
+                    if (vmask == 0u) continue;
+                    nvalid += __popc(vmask);
                     if (!valid) continue;
-                    any_valid = true;
                     float G0, G1, G2, GD, GW, NTBG;
                     if (G_IN_SMEM) {
                         const float4 g = lds128(s_g + (k * NT + tid) * 16);
@@ -443,57 +459,47 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                     } else {
                         G0 = g0[k]; G1 = g1[k]; G2 = g2[k]; GD = gd[k]; GW = gw[k]; NTBG = nTbg[k];
                     }
-                    // T_j = T_{j+1} / (1 - alpha); one reciprocal serves both divisions of backward.cu:1051,1090
+                    // T_j = T_{j+1} / (1 - alpha); one (approximate, 1-ulp) reciprocal serves both divisions of
+                    // backward.cu:1051,1090 -- see DESIGN.md, tolerance notes
                     const float rcp = __fdividef(1.0f, 1.f - alpha);
                     T[k] = T[k] * rcp;
                     const float dchannel_dcolor = alpha * T[k];
                     const float4 col = lds128(a + 32);
-                    const float one_minus_alpha = 1.f - alpha;
-                    float dL_dalpha = 0.0f;
-                    // ar* hold "colour behind this splat" (the reference's accum_rec after its update)
-                    dL_dalpha += (col.x - ar0[k]) * G0;
-                    dL_dalpha += (col.y - ar1[k]) * G1;
-                    dL_dalpha += (col.z - ar2[k]) * G2;
-                    v[GA_R] += dchannel_dcolor * G0;
-                    v[GA_G] += dchannel_dcolor * G1;
-                    v[GA_B] += dchannel_dcolor * G2;
-                    ar0[k] = alpha * col.x + one_minus_alpha * ar0[k];
-                    ar1[k] = alpha * col.y + one_minus_alpha * ar1[k];
-                    ar2[k] = alpha * col.z + one_minus_alpha * ar2[k];
-                    dL_dalpha += (q0.z - ad[k]) * GD;
-                    v[GA_DEPTH] += dchannel_dcolor * GD;
-                    ad[k] = alpha * q0.z + one_minus_alpha * ad[k];
-                    dL_dalpha += (1 - aa[k]) * GW;
-                    aa[k] = alpha + one_minus_alpha * aa[k];
-
-                    dL_dalpha *= T[k];
-                    dL_dalpha += NTBG * rcp;
-
-                    const float dL_dG = con_o.w * dL_dalpha;
-                    const float gdx = Gv * d.x;
-                    const float gdy = Gv * d.y;
-                    const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                    const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-                    const float mx = dL_dG * dG_ddelx * ddelx_dx;
-                    const float my = dL_dG * dG_ddely * ddely_dy;
-                    v[GA_MX] += mx;
-                    v[GA_MY] += my;
-                    v[GA_AMX] += fabsf(mx);
-                    v[GA_AMY] += fabsf(my);
-                    v[GA_CA] += -0.5f * gdx * d.x * dL_dG;
-                    v[GA_CB] += -0.5f * gdx * d.y * dL_dG;
-                    v[GA_CC] += -0.5f * gdy * d.y * dL_dG;
-                    v[GA_OP] += Gv * dL_dalpha;
-                    v[GA_COV] += con_o.x + con_o.z;  // diagnostic trace, once per contributing pixel (backward.cu:1116)
+                    v[GA_R] = fmaf(dchannel_dcolor, G0, v[GA_R]);
+                    v[GA_G] = fmaf(dchannel_dcolor, G1, v[GA_G]);
+                    v[GA_B] = fmaf(dchannel_dcolor, G2, v[GA_B]);
+                    v[GA_DEPTH] = fmaf(dchannel_dcolor, GD, v[GA_DEPTH]);
+                    // dL/dalpha.  The reference keeps five "colour behind this splat" recurrences (accum_rec per
+                    // channel, depth and weight; backward.cu:1060-1079) and sums (c - accum_rec) * dL_dchannel.  With
+                    // cg = sum_ch c_ch * dL_dchannel (depth and the weight's constant 1 included) the same quantity is
+                    //   T_j * cg_j - D_j / (1 - alpha_j),   D_j = sum_{i behind j} alpha_i T_i cg_i
+                    // -- one scalar recurrence instead of five.
+                    const float cg = fmaf(col.x, G0, fmaf(col.y, G1, fmaf(col.z, G2, fmaf(q0.z, GD, GW))));
+                    const float dL_dalpha = fmaf(T[k], cg, rcp * (NTBG - Dacc[k]));
+                    Dacc[k] = fmaf(dchannel_dcolor, cg, Dacc[k]);
+                    // Raw moments; the per-splat constants (opacity, 0.5 W, 0.5 H, -0.5) are applied once per
+                    // Gaussian by the backward preprocess instead of once per pixel here:
+                    //   dL_dmean2D.x = -o (W/2) sum q u      u = a dx + b dy        (backward.cu:1098-1103)
+                    //   dL_dconic.x  = -o/2 sum q dx^2 ...                          (backward.cu:1107-1110)
+                    //   dL_dopacity  = sum q,   q = G dL_dalpha                     (backward.cu:1113)
+                    const float q = Gv * dL_dalpha;
+                    const float mxq = q * fmaf(dy, con_o.y, adx);
+                    const float myq = q * fmaf(dy, con_o.z, bdx);
+                    v[GA_MX] += mxq;
+                    v[GA_MY] += myq;
+                    v[GA_AMX] += fabsf(mxq);
+                    v[GA_AMY] += fabsf(myq);
+                    const float qdx = q * dx, qdy = q * dy;
+                    v[GA_CA] = fmaf(qdx, dx, v[GA_CA]);
+                    v[GA_CB] = fmaf(qdx, dy, v[GA_CB]);
+                    v[GA_CC] = fmaf(qdy, dy, v[GA_CC]);
+                    v[GA_OP] += q;
                 }
 #ifdef BAGS_STATS
-                {
-                    const u32 vm = __ballot_sync(FULL, any_valid);
-                    if (lane == 0) atomicAdd(&g_stats[__popc(vm)], 1ull);
-                }
+                if (lane == 0) atomicAdd(&g_stats[min(nvalid, 63u)], 1ull);
 #endif
-                if (!__any_sync(FULL, any_valid)) continue;
-                warp_reduce_commit(v, lane, gacc + (size_t)lds32(s_id + j * 4) * GACC_STRIDE);
+                if (nvalid == 0u) continue;
+                warp_reduce_commit12(v, (float)nvalid, lane, gacc + (size_t)lds32(s_id + j * 4) * GACC_STRIDE);
             }
         }
     }

@@ -75,6 +75,17 @@ __device__ __forceinline__ void sh_tile_copy(float* tile, int stride, float* gpt
     }
 }
 
+// Scales that turn the raw moments accumulated by the blend backward into the reference's per-splat gradients.
+struct GradScale { float sx, sy, sc, trace; };
+__device__ __forceinline__ GradScale grad_scale(const float4 conic_opacity, const int W, const int H) {
+    GradScale g;
+    g.sx = conic_opacity.w * (0.5f * (float)W);
+    g.sy = conic_opacity.w * (0.5f * (float)H);
+    g.sc = -0.5f * conic_opacity.w;
+    g.trace = conic_opacity.x + conic_opacity.z;
+    return g;
+}
+
 struct Cov2DBack {
     float dL_dcov[6];
     float dL_dT00, dL_dT01, dL_dT02, dL_dT10, dL_dT11, dL_dT12;
@@ -245,15 +256,19 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
             const float4* ga = reinterpret_cast<const float4*>(gacc + i * GACC_STRIDE);
             const float4 g0 = ga[0], g1 = ga[1], g2 = ga[2];
             const float g_cov = gacc[i * GACC_STRIDE + GA_COV];
+            // The blend backward accumulates raw per-splat moments (see blend.cu); the per-splat constants of
+            // backward.cu:1002-1003,1098-1116 are applied here, once per Gaussian: opacity, ddelx_dx = 0.5 W,
+            // ddely_dy = 0.5 H, the -0.5 of the conic terms, and conic.x + conic.z per contributing pixel.
+            const GradScale gs = grad_scale(rec[3 * i + 1], W, H);
             float dL_dcolor[3] = {g0.x, g0.y, g0.z};
             const float dL_ddepth = g0.w;
-            const float dmx = g1.x, dmy = g1.y;          // dL_dmean2D (NDC units)
-            const float3 dL_dconic = {g2.x, g2.y, g2.z};
+            const float dmx = -gs.sx * g1.x, dmy = -gs.sy * g1.y;          // dL_dmean2D (NDC units)
+            const float3 dL_dconic = {gs.sc * g2.x, gs.sc * g2.y, gs.sc * g2.z};
             out_mean2D[0] = dmx; out_mean2D[1] = dmy;
-            out_dens[0] = g1.z; out_dens[1] = g1.w;
+            out_dens[0] = gs.sx * g1.z; out_dens[1] = gs.sy * g1.w;
             out_color[0] = g0.x; out_color[1] = g0.y; out_color[2] = g0.z;
             out_opacity = g2.w;
-            out_covariance = g_cov + 0.0001f;
+            out_covariance = g_cov * gs.trace + 0.0001f;
 
             const float3 m = {means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]};
             float cov6[6];
@@ -547,8 +562,9 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
 __global__ void pose_finalize_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ scales,
                                      const float* __restrict__ rotations, float scale_modifier,
                                      const float* __restrict__ cov3D_precomp, const float* __restrict__ viewmatrix,
-                                     float tan_fovx, float tan_fovy, float focal_x, float focal_y,
-                                     const float* __restrict__ gacc, const double* __restrict__ pose_acc, BwdOut o) {
+                                     float tan_fovx, float tan_fovy, float focal_x, float focal_y, int W, int H,
+                                     const float4* __restrict__ rec, const float* __restrict__ gacc,
+                                     const double* __restrict__ pose_acc, BwdOut o) {
     const int t = threadIdx.x;
     const float invP = (float)P;
     // sum rounded to fp32 once, then the reference's fp32 division by P (torch mean)
@@ -569,7 +585,8 @@ __global__ void pose_finalize_kernel(int P, const float* __restrict__ means3D, c
             float cov6[6];
             load_cov3d(idx, cov3D_precomp, scales, rotations, scale_modifier, cov6);
             const float* ga = gacc + i * GACC_STRIDE;
-            const float3 dL_dconic = {ga[GA_CA], ga[GA_CB], ga[GA_CC]};
+            const GradScale gs = grad_scale(rec[3 * i + 1], W, H);
+            const float3 dL_dconic = {gs.sc * ga[GA_CA], gs.sc * ga[GA_CB], gs.sc * ga[GA_CC]};
             const float dL_ddepth = ga[GA_DEPTH];
             const float* view_matrix = viewmatrix;
             const Cov2DBack cb = cov2d_backward(mean, cov6, focal_x, focal_y, tan_fovx, tan_fovy, view_matrix,
@@ -631,8 +648,8 @@ int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gac
         pose_acc, o, vec4, (u32)accumulate_mask);
     BAGS_LAUNCH_OK("preprocess_bwd_kernel");
     pose_finalize_kernel<<<1, 32, 0, st>>>(a.P, a.means3D, a.scales, a.rotations, a.scale_modifier, a.cov3D_precomp,
-                                           a.viewmatrix, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, gacc,
-                                           pose_acc, o);
+                                           a.viewmatrix, a.tan_fovx, a.tan_fovy, a.focal_x, a.focal_y, a.W, a.H,
+                                           g.rec, gacc, pose_acc, o);
     BAGS_LAUNCH_OK("pose_finalize_kernel");
     return 0;
 }

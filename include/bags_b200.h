@@ -326,7 +326,9 @@ int bags_adam_step(int ntensors, const bags_adam_tensor* tensors, double beta1, 
 /* Test-only view of the private state.  Any output pointer may be NULL.  All outputs are device pointers:
  *   tiles_touched [P] u32, depth_bits [P] u32 (float bits of the view-space depth, undefined for culled),
  *   xy [P,2] f32, conic_opacity [P,4] f32, rgb [P,3] f32,
- *   point_list [R] u32, point_list_keys [R] u64 (tile << 32 | depth bits, reconstructed), ranges [tiles,2] u32,
+ *   point_list [R] u32, point_list_keys [R] u64 (tile << 32 | depth bits, reconstructed; R = the slots of the binning
+ *   buffer: after an asynchronous forward that is the capacity, and the slots past the actual count read 0),
+ *   ranges [tiles,2] u32,
  *   n_contrib [H*W] u32, final_T [H*W] f32. */
 int bags_unpack_state(int P, int R, int width, int height,
                       const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
