@@ -7,6 +7,11 @@ nvcc/g++ commands (the reference's own setup.py / CMake are NOT run) into the gi
     oracle/_ref/diff_gaussian_rasterization/{__init__.py,_C.so}   <- 3dgs-pose/{cuda_rasterizer/*.cu,rasterize_points.cu,ext.cpp}
     oracle/_ref/simple_knn/{__init__.py,_C.so}                    <- simple-knn/{simple_knn.cu,spatial.cu,ext.cpp}
 
+    oracle/_ref/glue/{gaussian_renderer/__init__.py, scene/{cameras,gaussian_model}.py, utils/*.py}
+                                                                  <- the reference's own Python callers of the two
+                                                                     extensions, byte for byte (for the integration
+                                                                     test: render(), Camera, GaussianModel, losses)
+
 Nothing under oracle/_ref is product code: only tests/, __graft_entry__.smoke() and ``bench.py --impl reference``
 import it, as the thing the product is compared against.  The only Python file copied is the reference's own
 autograd wrapper (needed to call the reference through its public API on the GPU box, where /root/reference does
@@ -77,6 +82,28 @@ def build_ext(name, srcdir, sources, extra_inc, pyfiles):
     return so
 
 
+GLUE_FILES = [
+    "gaussian_renderer/__init__.py",         # render(): builds the settings tuple, calls the rasterizer, 5-value unpack
+    "scene/cameras.py",                      # Camera: learnable delta_quaternion / delta_translation / fov -> matrices
+    "scene/gaussian_model.py",               # GaussianModel: activations, create_from_pcd -> distCUDA2
+    "utils/graphics_utils.py", "utils/general_utils.py", "utils/sh_utils.py", "utils/system_utils.py",
+    "utils/rigid_utils.py", "utils/camera.py", "utils/loss_utils.py",
+]
+
+
+def stage_glue():
+    """Copies the reference's Python callers of the extensions, unmodified, into the git-ignored oracle/_ref/glue so
+    that tests/test_reference_glue_gpu.py can run them on the GPU box (where /root/reference does not exist) on top
+    of both implementations.  scene/__init__.py is deliberately NOT staged: `scene` becomes a namespace package, so
+    importing scene.cameras does not drag in the dataset readers and lens networks (out of scope, missing packages)."""
+    for rel in GLUE_FILES:
+        src = os.path.join(REF, rel)
+        dst = os.path.join(OUT, "glue", rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(src, dst)
+    print(f"[build_ref] staged {len(GLUE_FILES)} reference Python files under {os.path.join(OUT, 'glue')}")
+
+
 def main():
     if not os.path.isdir(REF):
         print(f"[build_ref] {REF} not present -- using prebuilt oracle/_ref if any")
@@ -94,6 +121,7 @@ def main():
     init = os.path.join(OUT, "simple_knn", "__init__.py")
     if not os.path.exists(init):
         open(init, "w").close()
+    stage_glue()
     return 0
 
 

@@ -26,6 +26,8 @@ bit for bit.
 """
 import math
 
+import contextlib
+
 import torch
 
 F64 = torch.float64
@@ -38,8 +40,27 @@ SH_C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.37317633
 TILE = 16
 
 
+# Where the oracle computes.  The CPU is the default (tests without a GPU, bench.py's cpu_baseline); the full-size
+# pose-gradient checks run the same float64 code on the GPU (`with on_device("cuda"):`) because 10^6 Gaussians at 1080p
+# take minutes on host cores.  Still test infrastructure either way: nothing here is reachable from the product.
+DEVICE = "cpu"
+
+
+@contextlib.contextmanager
+def on_device(dev):
+    """Runs the oracle on `dev`: inputs are moved there in float64 and every tensor the oracle creates is allocated
+    there (torch's device context manager covers the factory calls)."""
+    global DEVICE
+    prev, DEVICE = DEVICE, str(dev)
+    try:
+        with torch.device(dev):
+            yield
+    finally:
+        DEVICE = prev
+
+
 def _d(x):
-    return None if x is None else x.detach().to("cpu", F64)
+    return None if x is None else x.detach().to(DEVICE, F64)
 
 
 def _xform4x3(p, m):
@@ -298,9 +319,10 @@ def blend_forward(sc, pre, point_list, ranges):
     alpha_img = torch.zeros(H, W, dtype=F64)
     final_T = torch.ones(H, W, dtype=F64)
     n_contrib = torch.zeros(H, W, dtype=torch.int64)
+    ranges_host = ranges.tolist()
     for t in range(sc.gx * sc.gy):
         xx, yy = _tile_pixels(sc, t)
-        s, e = int(ranges[t, 0]), int(ranges[t, 1])
+        s, e = ranges_host[t]
         if e > s:
             ids = point_list[s:e]
             dx, dy, G, alpha, live, T_before, T_incl, stop = _tile_alpha(sc, pre, ids, xx, yy)
@@ -339,8 +361,9 @@ def blend_backward(sc, pre, point_list, ranges, dL_dcolor, dL_ddepth, dL_dalpha)
                dL_dconic=torch.zeros(P, 3, dtype=F64), covariance=torch.zeros(P, dtype=F64),
                dL_dopacity=torch.zeros(P, dtype=F64))
     ddelx_dx, ddely_dy = 0.5 * sc.W, 0.5 * sc.H
+    ranges_host = ranges.tolist()
     for t in range(sc.gx * sc.gy):
-        s, e = int(ranges[t, 0]), int(ranges[t, 1])
+        s, e = ranges_host[t]
         if e <= s:
             continue
         xx, yy = _tile_pixels(sc, t)
