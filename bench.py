@@ -73,7 +73,14 @@ def parse(argv=None):
     ap.add_argument("--torch-loss", action="store_true",
                     help="e2e leg of our arm: the torch operator sequence of utils/loss_utils.py:18-19 (what the "
                          "reference arm always runs) instead of bags_loss.l1_loss_u8")
+    ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
+                    help="development: bags_set_tuning knob (BLEND_FWD_PPT, BLEND_BWD_PPT, BLEND_CULL, SORT_LOOKBACK, "
+                         "SORT_SMALL_TILES, SORT_HWMATCH, PBWD_MIN_BLOCKS, BLEND_STAGING) before anything runs")
     return ap.parse_args(argv)
+
+
+TUNE_KNOBS = {"BLEND_FWD_PPT": 0, "BLEND_BWD_PPT": 1, "BLEND_CULL": 2, "SORT_LOOKBACK": 3, "SORT_SMALL_TILES": 4,
+              "SORT_HWMATCH": 5, "PBWD_MIN_BLOCKS": 6, "BLEND_STAGING": 7}
 
 
 def load_impl(name):
@@ -391,8 +398,13 @@ def main():
         loss_dev[buf].copy_(torch.stack(losses).sum().reshape(1))
 
     capi = None
+    tuned = {}
     if ours:
         import bags_capi as capi
+        for kv in args.tune:
+            k, v = kv.split("=")
+            capi.check(capi.lib().bags_set_tuning(TUNE_KNOBS[k], int(v)), "bags_set_tuning")
+            tuned[k] = int(v)
     launches_per_step = None
     cap_dev = cap_e2e = None
     if graph_mode:
@@ -685,6 +697,8 @@ def main():
         else "autograd (fresh gradient tensors + add)",
         "allreduce": (overlap.describe() if overlap is not None else "one all_reduce after the step") if use_dist
         else None}
+    if tuned:
+        line["implementation"]["tuning"] = tuned
     line["e2e"] = e2e
     if drop_in is not None:
         line["drop_in"] = drop_in

@@ -39,6 +39,7 @@ constexpr u32 FULL = 0xffffffffu;
 static int g_fwd_ppt = 2;
 static int g_bwd_ppt = 2;
 static int g_cull = 1;   // 0: every splat of the tile list is evaluated for every patch (debugging / tests)
+static int g_staging = 0;   // 1: cp.async double-buffered batch staging (see stage_issue); 0: ldg -> sts, one buffer
 
 // Tile decomposition.  Cell grid: 4 columns of 4 pixels x 8 rows of 2 pixels, bit = row * 4 + column.  Patch (x, y),
 // x in 0..1, y in 0..3, is the 8x4 pixel block at (8x, 4y) = cells {2x, 2x+1} x {2y, 2y+1} = bits 0x33 << (8y + 2x).
@@ -138,17 +139,50 @@ __device__ __forceinline__ void stage_batch(const u32* __restrict__ point_list, 
     }
 }
 
-template <int PPT>
+// ---- asynchronous staging (BAGS_TUNE_BLEND_STAGING = 1) --------------------------------------------------------------
+// The batch's records go from global to shared memory with cp.async (LDGSTS: no register round trip) into one of two
+// buffers, one batch ahead of the one being blended; the cell masks are computed from shared memory once the copies
+// of the batch have landed.
+__device__ __forceinline__ void cp_async16(const u32 smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NT, bool WITH_ID>
+__device__ __forceinline__ void stage_issue(const u32* __restrict__ point_list, const float4* __restrict__ rec,
+                                            const u32 first, const int dir, const int cnt, const u32 s_rec,
+                                            u32* sm_id) {
+    for (int s = threadIdx.x; s < cnt; s += NT) {
+        const u32 id = point_list[first + (u32)(dir * s)];
+        const float4* r = rec + 3 * (size_t)id;
+        if (WITH_ID) sm_id[s] = id;
+        cp_async16(s_rec + s * 48, r);
+        cp_async16(s_rec + s * 48 + 16, r + 1);
+        cp_async16(s_rec + s * 48 + 32, r + 2);
+    }
+}
+template <int NT>
+__device__ __forceinline__ void stage_finish(const int cnt, const float tx0, const float ty0, const u32 s_rec,
+                                             u32* sm_cell, const bool cull) {
+    for (int s = threadIdx.x; s < cnt; s += NT)
+        sm_cell[s] = cull ? splat_cellmask(lds128(s_rec + s * 48), lds128(s_rec + s * 48 + 16), tx0, ty0)
+                          : 0xffffffffu;
+}
+
+template <int PPT, bool ASYNC>
 __global__ void __launch_bounds__(256 / PPT)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float4* __restrict__ rec, float* __restrict__ final_T, u32* __restrict__ n_contrib,
                  const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_depth,
                  float* __restrict__ out_alpha, const bool cull) {
     constexpr int NT = 256 / PPT;
-    __shared__ __align__(16) float4 sm_rec[BATCH * 3];
-    __shared__ u32 sm_cell[BATCH];
-    const u32 s_rec = smem_addr(sm_rec);
-    const u32 s_cell = smem_addr(sm_cell);
+    constexpr int NBUF = ASYNC ? 2 : 1;
+    __shared__ __align__(16) float4 sm_rec[NBUF][BATCH * 3];
+    __shared__ u32 sm_cell[NBUF][BATCH];
+    const u32 s_rec0 = smem_addr(sm_rec);
+    const u32 s_cell0 = smem_addr(sm_cell);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const WarpPixels<PPT> wp(tid >> 5);
@@ -176,16 +210,32 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     const int rounds = ((range.y - range.x + BATCH - 1) / BATCH);
     int toDo = range.y - range.x;
 
+    if (ASYNC && rounds > 0) {
+        stage_issue<NT, false>(point_list, rec, range.x, 1, min(BATCH, toDo), s_rec0, nullptr);
+        cp_async_commit();
+    }
     for (int i = 0; i < rounds; i++, toDo -= BATCH) {
         bool all_done = true;
 #pragma unroll
         for (int k = 0; k < PPT; k++) all_done = all_done && done[k];
-        const int num_done = __syncthreads_count(all_done);
+        const int num_done = __syncthreads_count(all_done);   // also: everyone has left batch i-1's buffer
         if (num_done == NT) break;
 
         const int cnt = min(BATCH, toDo);
-        stage_batch<NT, false>(point_list, rec, range.x + (u32)(i * BATCH), 1, cnt, tx0, ty0, sm_rec, sm_cell, nullptr,
-                               cull);
+        const int buf = ASYNC ? (i & 1) : 0;
+        const u32 s_rec = s_rec0 + buf * (BATCH * 48);
+        const u32 s_cell = s_cell0 + buf * (BATCH * 4);
+        if (ASYNC) {
+            if (i + 1 < rounds)
+                stage_issue<NT, false>(point_list, rec, range.x + (u32)((i + 1) * BATCH), 1, min(BATCH, toDo - BATCH),
+                                       s_rec0 + (buf ^ 1) * (BATCH * 48), nullptr);
+            cp_async_commit();                                // (possibly empty) group of batch i+1
+            cp_async_wait<1>();                               // this thread's copies of batch i have landed
+            stage_finish<NT>(cnt, tx0, ty0, s_rec, sm_cell[buf], cull);
+        } else {
+            stage_batch<NT, false>(point_list, rec, range.x + (u32)(i * BATCH), 1, cnt, tx0, ty0, sm_rec[0], sm_cell[0],
+                                   nullptr, cull);
+        }
         __syncthreads();
 
         // cells of the patches that still have unfinished pixels
@@ -242,6 +292,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
         }
     }
 
+    if (ASYNC) cp_async_wait<0>();   // nothing may be in flight into shared memory when the CTA retires
     const size_t plane = (size_t)H * W;
     const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 #pragma unroll
@@ -261,13 +312,19 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
     dim3 grid(tiles_x(W), tiles_y(H), 1);
-#define BAGS_FWD(PPT)                                                                                            \
-    blend_fwd_kernel<PPT><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, g.rec, img.final_T,        \
-                                                     img.n_contrib, bg, out_color, out_depth, out_alpha,       \
-                                                     g_cull != 0)
-    if (g_fwd_ppt == 4) BAGS_FWD(4);
-    else if (g_fwd_ppt == 2) BAGS_FWD(2);
-    else BAGS_FWD(1);
+#define BAGS_FWD(PPT, ASYNC)                                                                                     \
+    blend_fwd_kernel<PPT, ASYNC><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, g.rec, img.final_T, \
+                                                            img.n_contrib, bg, out_color, out_depth, out_alpha, \
+                                                            g_cull != 0)
+    if (g_staging) {
+        if (g_fwd_ppt == 4) BAGS_FWD(4, true);
+        else if (g_fwd_ppt == 2) BAGS_FWD(2, true);
+        else BAGS_FWD(1, true);
+    } else {
+        if (g_fwd_ppt == 4) BAGS_FWD(4, false);
+        else if (g_fwd_ppt == 2) BAGS_FWD(2, false);
+        else BAGS_FWD(1, false);
+    }
 #undef BAGS_FWD
     BAGS_LAUNCH_OK("blend_fwd_kernel");
     return 0;
@@ -326,7 +383,7 @@ __device__ __forceinline__ void warp_reduce_commit12(const float (&v)[12], const
 __device__ unsigned long long g_stats[64];
 #endif
 
-template <int PPT>
+template <int PPT, bool ASYNC>
 __global__ void __launch_bounds__(256 / PPT)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float* __restrict__ bg_color, const float4* __restrict__ rec,
@@ -335,13 +392,14 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                  const float* __restrict__ dL_dalphas, float* __restrict__ gacc, const bool cull) {
     constexpr int NT = 256 / PPT;
     constexpr int NW = NT / 32;
-    __shared__ __align__(16) float4 sm_rec[BATCH * 3];
-    __shared__ u32 sm_cell[BATCH];
-    __shared__ u32 sm_id[BATCH];
+    constexpr int NBUF = ASYNC ? 2 : 1;
+    __shared__ __align__(16) float4 sm_rec[NBUF][BATCH * 3];
+    __shared__ u32 sm_cell[NBUF][BATCH];
+    __shared__ u32 sm_id[NBUF][BATCH];
     __shared__ u32 s_wmax[NW];
-    const u32 s_rec = smem_addr(sm_rec);
-    const u32 s_cell = smem_addr(sm_cell);
-    const u32 s_id = smem_addr(sm_id);
+    const u32 s_rec0 = smem_addr(sm_rec);
+    const u32 s_cell0 = smem_addr(sm_cell);
+    const u32 s_id0 = smem_addr(sm_id);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const WarpPixels<PPT> wp(warp);
@@ -407,11 +465,30 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     for (int w = 0; w < NW; w++) block_max = max(block_max, s_wmax[w]);
 
     // walk positions [0, block_max) back to front in chunks of BATCH; slot j of a chunk is position hi-1-j
-    for (int hi = (int)block_max; hi > 0; hi -= BATCH) {
+    if (ASYNC && block_max > 0) {
+        stage_issue<NT, true>(point_list, rec, range.x + (u32)(block_max - 1), -1, min(BATCH, (int)block_max), s_rec0,
+                              sm_id[0]);
+        cp_async_commit();
+    }
+    int it = 0;
+    for (int hi = (int)block_max; hi > 0; hi -= BATCH, it++) {
         const int cnt = min(BATCH, hi);
+        const int buf = ASYNC ? (it & 1) : 0;
+        const u32 s_rec = s_rec0 + buf * (BATCH * 48);
+        const u32 s_cell = s_cell0 + buf * (BATCH * 4);
+        const u32 s_id = s_id0 + buf * (BATCH * 4);
         __syncthreads();  // everyone is done with the previous chunk
-        stage_batch<NT, true>(point_list, rec, range.x + (u32)(hi - 1), -1, cnt, tx0, ty0, sm_rec, sm_cell, sm_id,
-                              cull);
+        if (ASYNC) {
+            if (hi > BATCH)
+                stage_issue<NT, true>(point_list, rec, range.x + (u32)(hi - BATCH - 1), -1, min(BATCH, hi - BATCH),
+                                      s_rec0 + (buf ^ 1) * (BATCH * 48), sm_id[buf ^ 1]);
+            cp_async_commit();
+            cp_async_wait<1>();
+            stage_finish<NT>(cnt, tx0, ty0, s_rec, sm_cell[buf], cull);
+        } else {
+            stage_batch<NT, true>(point_list, rec, range.x + (u32)(hi - 1), -1, cnt, tx0, ty0, sm_rec[0], sm_cell[0],
+                                  sm_id[0], cull);
+        }
         __syncthreads();
 
         // first slot this warp can contribute to: position hi-1-j < warp_max  <=>  j >= hi-warp_max
@@ -503,19 +580,26 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
             }
         }
     }
+    if (ASYNC) cp_async_wait<0>();
 }
 
 int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, const ImageState& img, const float* bg,
                      const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalpha, float* gacc,
                      cudaStream_t st) {
     dim3 grid(tiles_x(W), tiles_y(H), 1);
-#define BAGS_BWD(PPT)                                                                                            \
-    blend_bwd_kernel<PPT><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec, img.final_T,    \
-                                                     img.n_contrib, dL_dpix, dL_dpix_depth, dL_dalpha, gacc,   \
-                                                     g_cull != 0)
-    if (g_bwd_ppt == 4) BAGS_BWD(4);
-    else if (g_bwd_ppt == 2) BAGS_BWD(2);
-    else BAGS_BWD(1);
+#define BAGS_BWD(PPT, ASYNC)                                                                                     \
+    blend_bwd_kernel<PPT, ASYNC><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec,          \
+                                                            img.final_T, img.n_contrib, dL_dpix, dL_dpix_depth, \
+                                                            dL_dalpha, gacc, g_cull != 0)
+    if (g_staging) {
+        if (g_bwd_ppt == 4) BAGS_BWD(4, true);
+        else if (g_bwd_ppt == 2) BAGS_BWD(2, true);
+        else BAGS_BWD(1, true);
+    } else {
+        if (g_bwd_ppt == 4) BAGS_BWD(4, false);
+        else if (g_bwd_ppt == 2) BAGS_BWD(2, false);
+        else BAGS_BWD(1, false);
+    }
 #undef BAGS_BWD
     BAGS_LAUNCH_OK("blend_bwd_kernel");
     return 0;
@@ -539,6 +623,11 @@ extern "C" int bags_set_tuning(int knob, int value) {
     if (knob == BAGS_TUNE_BLEND_CULL) {
         const int prev = bags::g_cull;
         if (value == 0 || value == 1) bags::g_cull = value;
+        return prev;
+    }
+    if (knob == BAGS_TUNE_BLEND_STAGING) {
+        const int prev = bags::g_staging;
+        if (value == 0 || value == 1) bags::g_staging = value;
         return prev;
     }
     if (knob == BAGS_TUNE_SORT_LOOKBACK) return bags::set_sort_lookback(value);

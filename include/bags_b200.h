@@ -365,11 +365,14 @@ int bags_profile_read(double* ms, unsigned long long* calls);
  * round (4 or 8; default 4; no effect on results).  SORT_SMALL_TILES: 1 (default) sorts 2048 instead of 4096 keys
  * per CTA when a pass would not fill the GPU twice (latency-bound sizes, e.g. the 1 M-key depth sort); SORT_HWMATCH: 1
  * ranks those small tiles with match.any instead of one vote per digit bit (default 0).  PBWD_MIN_BLOCKS: resident CTAs
- * per SM the backward preprocess kernel is compiled for (5 = 96 registers; 6 = 80 registers, default).  Returns the previous value (other values only
+ * per SM the backward preprocess kernel is compiled for (5 = 96 registers; 6 = 80 registers, default).  BLEND_STAGING: how
+ * the blend kernels bring a batch of splat records into shared memory -- 0 (default): ldg -> registers -> sts, one
+ * buffer; 1: cp.async (LDGSTS) into two alternating buffers, one batch ahead of the one being blended (same results;
+ * measured in profiles/).  Returns the previous value (other values only
  * query), BAGS_E_INVALID for an unknown knob. */
 enum { BAGS_TUNE_BLEND_FWD_PPT = 0, BAGS_TUNE_BLEND_BWD_PPT = 1, BAGS_TUNE_BLEND_CULL = 2,
        BAGS_TUNE_SORT_LOOKBACK = 3, BAGS_TUNE_SORT_SMALL_TILES = 4, BAGS_TUNE_SORT_HWMATCH = 5,
-       BAGS_TUNE_PBWD_MIN_BLOCKS = 6 };
+       BAGS_TUNE_PBWD_MIN_BLOCKS = 6, BAGS_TUNE_BLEND_STAGING = 7 };
 int bags_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

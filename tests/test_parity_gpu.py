@@ -144,10 +144,11 @@ def test_against_live_reference(case):
 
 
 @pytest.mark.skipif(not pc.ref_available(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("staging", [0, 1], ids=["ldg_sts", "cp_async"])
 @pytest.mark.parametrize("ppt", [1, 2, 4])
 @pytest.mark.parametrize("case", [LIVE_CASES[1], LIVE_CASES[3]], ids=["bg_shift", "dense_big_splats"])
-def test_blend_pixels_per_thread_live(case, ppt):
-    """Every pixels-per-thread variant of the blend kernels (bags_set_tuning) meets the same bars."""
+def test_blend_pixels_per_thread_live(case, ppt, staging):
+    """Every pixels-per-thread and batch-staging variant of the blend kernels (bags_set_tuning) meets the same bars."""
     import bags_capi
     L = bags_capi.lib()
     cam = S.make_camera(case["W"], case["H"])
@@ -156,11 +157,13 @@ def test_blend_pixels_per_thread_live(case, ppt):
     kw = dict(sh_degree=case.get("sh_degree", 3), bg=case.get("bg", (0, 0, 0)), shift=case.get("shift", (0, 0, 0)),
               scale_modifier=case.get("scale_modifier", 1.0))
     prev = [L.bags_set_tuning(knob, ppt) for knob in (0, 1)]
+    prev_staging = L.bags_set_tuning(7, staging)
     try:
         o = pc.run_view(pc.load_ours(), cam, gs, up, dev(), **kw)
     finally:
         for knob in (0, 1):
             L.bags_set_tuning(knob, prev[knob])
+        L.bags_set_tuning(7, prev_staging)
     r = pc.run_view(pc.load_ref(), cam, gs, up, dev(), **kw)
     _check_live(o, r, (cam, gs, up, kw))
 

@@ -14,6 +14,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.004
 impl = sys.argv[3] if len(sys.argv) > 3 else "ours"       # "ref": the unmodified reference build (oracle/_ref)
 mod = pc.load_ref() if impl == "ref" else pc.load_ours()
+if impl != "ref" and os.environ.get("BAGS_NCU_STAGING"):
+    import bags_capi
+    bags_capi.lib().bags_set_tuning(7, int(os.environ["BAGS_NCU_STAGING"]))
 c = S.CONFIGS["C3"]
 cam0 = S.make_camera(c["W"], c["H"], seed=100)
 gs = S.make_gaussians(c["P"], cam0, scale=scale)
