@@ -409,7 +409,8 @@ def main():
     cap_dev = cap_e2e = None
     if graph_mode:
         clear_pose_grads()
-        cap_dev = VP.CapturedStep(body_device, dev, mod, capacity, forwards_per_step=len(views))
+        cap_dev = VP.CapturedStep(body_device, dev, mod, capacity, forwards_per_step=len(views),
+                                  reset=clear_pose_grads)
         # kernels of ours inside one step (what one replay launches): counted on an eager run of the same enqueue
         with mod.AsyncForward(capacity, slots=len(views)):
             l0 = capi.lib().bags_launch_count()
@@ -600,8 +601,8 @@ def main():
     if not args.no_e2e:
         if graph_mode:
             clear_pose_grads()
-            cap_e2e = [VP.CapturedStep(lambda b=b: body_e2e(b), dev, mod, capacity, forwards_per_step=len(views))
-                       for b in range(2)]
+            cap_e2e = [VP.CapturedStep(lambda b=b: body_e2e(b), dev, mod, capacity, forwards_per_step=len(views),
+                                      reset=clear_pose_grads) for b in range(2)]
         for _ in range(max(args.warmup, 3)):
             step_e2e()
         finish_e2e()

@@ -68,6 +68,8 @@ SIGNATURES = {
     "bags_l1_u8_scratch_bytes": (c_size_t, [ctypes.c_longlong]),
     "bags_l1_u8_forward": (c_int, [_P, _P, ctypes.c_longlong, _P, _P, _P, _P]),
     "bags_adam_step": (c_int, [c_int, c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, _P]),
+    "bags_densify_gather": (c_int, [ctypes.c_longlong, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int,
+                                    c_void_p, _P]),
     "bags_loss_forward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "bags_unpack_state": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P,
@@ -85,6 +87,12 @@ class AdamTensor(ctypes.Structure):
     """struct bags_adam_tensor of include/bags_b200.h"""
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
                 ("n", ctypes.c_longlong), ("step_size", ctypes.c_double), ("bias_correction2_sqrt", ctypes.c_double)]
+
+
+class DensifyTensor(ctypes.Structure):
+    """struct bags_densify_tensor of include/bags_b200.h"""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("src_m", c_void_p), ("dst_m", c_void_p), ("src_v", c_void_p),
+                ("dst_v", c_void_p), ("width", c_int), ("role", c_int)]
 
 
 STAGES = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges", "blend_fwd", "bwd_clear", "blend_bwd",

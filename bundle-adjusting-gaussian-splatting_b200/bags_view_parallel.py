@@ -398,12 +398,15 @@ class CapturedStep:
 
     `body()` must be capturable: static input tensors (camera matrices, ground truth, parameters are read from fixed
     addresses -- update them with copy_()), no host synchronisation, gradients of the Gaussian parameters accumulated
-    through gradient sinks or into pre-attached `.grad` buffers.  Per-camera leaves should have `.grad = None` before
-    the capture so that their gradient tensors come from the graph's private pool and are rewritten by every replay.
+    through gradient sinks or into pre-attached `.grad` buffers.  Leaves whose gradient autograd accumulates itself
+    (per-camera pose / intrinsic tensors, shift_factors) must have `.grad = None` when the capture starts, so that
+    their gradient tensors come from the graph's private pool and are REWRITTEN by every replay -- with a `.grad`
+    already in place autograd captures `grad += new` and the replays pile up.  `reset` (a callable that sets those
+    `.grad`s to None) is invoked before every warm-up run and before the capture.
     The tile-instance counts of the step's forwards land in `step.counts` (pinned int64[forwards_per_step])."""
 
     def __init__(self, body: Callable, device, rasterizer_module, capacity: int, forwards_per_step: int,
-                 warmup: int = 2):
+                 warmup: int = 2, reset: Callable = None):
         self.device = torch.device(device)
         self.af = rasterizer_module.AsyncForward(capacity, slots=max(1, int(forwards_per_step)))
         self.capacity = int(capacity)
@@ -413,11 +416,15 @@ class CapturedStep:
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):      # eager runs: lazy initialisations happen outside the capture
                 self.af._k = 0
+                if reset is not None:
+                    reset()
                 with self.af:
                     body()
         main.wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.af.check()
+        if reset is not None:
+            reset()
         self.graph = torch.cuda.CUDAGraph()
         self.af._k = 0
         with torch.cuda.graph(self.graph):

@@ -18,6 +18,9 @@
  *                                    that --outside_rasterizer runs on every rendered canvas
  *   bags_loss_forward/backward    <- utils/loss_utils.py:18-19 (l1_loss) and :49-76 (ssim / _ssim: five grouped 11x11
  *                                    Gaussian convolutions + the SSIM map), combined at train.py:325
+ *   bags_densify_gather           <- GaussianModel.densify_and_prune's torch.cat / masked-index surgery over the parameters
+ *                                    and Adam moments, scene/gaussian_model.py:315-447
+ *   bags_adam_step                <- torch.optim.Adam.step() as scene/gaussian_model.py:197-206 / train.py:420 use it
  *   bags_rasterize_forward_async  <- the same forward without the blocking read-back of num_rendered
  *                                    (rasterizer_impl.cu:291): caller-provided binning capacity, count kept on the device
  *   bags_unpack_state             (test-only) exposes the private binning/image state so parity tests can compare
@@ -322,6 +325,32 @@ typedef struct bags_adam_tensor {
     double bias_correction2_sqrt;
 } bags_adam_tensor;
 int bags_adam_step(int ntensors, const bags_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream);
+
+/* Fused densification compaction.  Replaces the tensor surgery of
+ * GaussianModel.densify_and_prune (scene/gaussian_model.py:334-447: densify_and_clone + densify_and_split +
+ * prune_points, each a torch.cat / boolean indexing of every parameter tensor and of both Adam moments) by ONE gather.
+ * The caller decides, per ORIGINAL row, with the reference's own mask expressions: keep (not a split parent, not
+ * pruned), clone (copy survives), child (split parent whose children survive); `flags` [P] holds them as bits 0/1/2
+ * (bit 3 = split parent, needed for the sample rank), `plan` [P][4] int32 the exclusive scans of the four bits, and
+ * kept / clones / children / split_parents their totals.  Output rows: [kept | clones | children r=0 | ... | r=N-1],
+ * every segment in ascending source row = the order the reference's cat + masked indexing produces.
+ * Per tensor (host array of descriptors, device pointers inside): rows of `width` floats; role 0 = plain copy,
+ * role 1 = xyz (child: R(rotation/|rotation|) . samples[r * split_parents + rank] + xyz), role 2 = log-scaling (child:
+ * log(exp(s) / (0.8 N))).  src_m/src_v (+dst) = Adam exp_avg / exp_avg_sq or NULL: copied for kept rows, zero for new
+ * rows.  `rotation` [P,4] raw quaternions, `samples` [N * split_parents, 3] the caller's torch.normal draws. */
+typedef struct bags_densify_tensor {
+    const float* src;
+    float* dst;
+    const float* src_m;
+    float* dst_m;
+    const float* src_v;
+    float* dst_v;
+    int width;
+    int role;
+} bags_densify_tensor;
+int bags_densify_gather(long long P, int N, const int32_t* plan, const uint8_t* flags, int kept, int clones,
+                        int children, int split_parents, const float* rotation, const float* samples, int ntensors,
+                        const bags_densify_tensor* tensors, void* stream);
 
 /* Test-only view of the private state.  Any output pointer may be NULL.  All outputs are device pointers:
  *   tiles_touched [P] u32, depth_bits [P] u32 (float bits of the view-space depth, undefined for culled),

@@ -95,12 +95,15 @@ def main():
                 stats.add_view(m2d.grad, m2dd.grad, radii)
                 m2d_grads[v] = m2d.grad
 
-    shift.grad = None
-    if rank % 2 == 1:
+    def clear():
+        shift.grad = None
         for v in mine:
             for t in leaves[v][:3]:
                 t.grad = None
-        step = VP.CapturedStep(body, dev, mod, capacity=6_000_000, forwards_per_step=len(mine))
+
+    clear()
+    if rank % 2 == 1:
+        step = VP.CapturedStep(body, dev, mod, capacity=6_000_000, forwards_per_step=len(mine), reset=clear)
         step.replay()
         torch.cuda.synchronize()
         step.check()

@@ -159,7 +159,7 @@ def test_captured_step_equals_eager_step(streams):
         img_eager = [i.clone() for i in images]
         pose_eager = [torch.cat([v.grad.flatten(), p.grad.flatten(), c.grad]).clone() for v, p, c, _ in leaves]
         clear()
-        step = VP.CapturedStep(body, d, mod, capacity=2_000_000, forwards_per_step=3)
+        step = VP.CapturedStep(body, d, mod, capacity=2_000_000, forwards_per_step=3, reset=clear)
         for rep in range(3):
             params.flat_grad.fill_(123.0)                        # the replay must start from its own zero_grad
             step.replay()
