@@ -207,3 +207,50 @@ def compare(ours, ref, verbose=True, check_rgb=True):
         for k, v in m.items():
             print(f"    {k}: {v}")
     return m
+
+
+# ---- pose / intrinsic gradients: the float64 oracle arbitrates --------------------------------------------------------
+POSE_ORACLE_KEYS = {"campos": "dL_dcampos", "projmatrix": "dL_dprojmatrix", "shift_factors": "dL_dshift"}
+
+
+def oracle_pose_grads(cam, gs, up, device, bg=(0.0, 0.0, 0.0), shift=(0.0, 0.0, 0.0), sh_degree=3,
+                      scale_modifier=1.0):
+    """The three reduced pose / intrinsic gradients from the float64 oracle, evaluated on `device`."""
+    import sys as _sys
+    if ROOT not in _sys.path:
+        _sys.path.insert(0, ROOT)
+    from oracle import raster_oracle as O
+    with O.on_device(str(device)):
+        sc = O.Scene(gs.means3D, gs.opacities, cam.viewmatrix, cam.projmatrix, cam.campos, cam.W, cam.H, cam.tanfovx,
+                     cam.tanfovy, bg, shs=gs.shs, scales=gs.scales, rotations=gs.rotations,
+                     shift_factors=torch.as_tensor(shift, dtype=torch.float32), sh_degree=sh_degree,
+                     scale_modifier=scale_modifier)
+        f = O.rasterize_forward(sc)
+        b = O.rasterize_backward(sc, f, *up)
+    return {k: b[ok].detach().cpu().reshape(-1) for k, ok in POSE_ORACLE_KEYS.items()}
+
+
+def check_pose_grads(ours, ref, make_oracle, tol=1e-4, report=None):
+    """Bar for dL_dcampos / dL_dprojmatrix / dL_dshift (means over all P rows of signed, heavily cancelling terms).
+
+    1. ours vs the live reference at the normal bar: relative L2 <= tol.
+    2. Where the two fp32 implementations differ by more than that, neither can be called right by comparing them with
+       each other (the measured distance of EITHER from a float64 evaluation of the same formulas is ~1e-4 on these
+       sums: profiles/r02_pose_oracle_*.jsonl).  The float64 oracle arbitrates: ours must be no farther from float64
+       than the reference is -- allowing a quarter of that distance plus 2e-5 for the run-to-run atomic-order noise of
+       both.  `make_oracle()` is only called in that case (it costs seconds at full size).
+    There is no looser fallback."""
+    oracle = None
+    for k in POSE_ORACLE_KEYS:
+        a, b = ours[k].detach().cpu().reshape(-1), ref[k].detach().cpu().reshape(-1)
+        e = rel_l2(a, b)
+        if report is not None:
+            report["pose_" + k + "_vs_reference"] = e
+        if e <= tol:
+            continue
+        if oracle is None:
+            oracle = make_oracle()
+        eo, er = rel_l2(a, oracle[k]), rel_l2(b, oracle[k])
+        if report is not None:
+            report["pose_" + k + "_vs_float64"] = (eo, er)
+        assert eo <= 1.25 * er + 2e-5, (k, "ours vs reference", e, "ours vs float64", eo, "reference vs float64", er)

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def run_bench(extra, steps):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(steps), "--warmup", "3",
-           "--no-cpu-baseline", "--no-e2e", *extra]
+           "--no-cpu-baseline", "--no-e2e", "--no-drop-in", "--min-seconds", "1", *extra]
     r = subprocess.run(cmd, capture_output=True, text=True)
     for line in r.stdout.splitlines()[::-1]:
         if line.startswith("{"):
@@ -65,7 +65,7 @@ def main():
     ap.add_argument("--skip-ref", action="store_true")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
-    keep = ("metric", "value", "ms_per_step", "ms_per_step_regions", "config", "stages", "preprocess_binning", "impl", "error", "clocks")
+    keep = ("metric", "value", "ms_per_step", "ms_per_step_regions", "config", "workload_stats", "stages", "preprocess_binning", "impl", "error", "clocks")
     with open(a.out, "w") as f:
         def emit(tag, line):
             line = {k: v for k, v in line.items() if k in keep}
