@@ -54,9 +54,14 @@ def parse(argv=None):
                     help="median Gaussian scale; 0.012 is the blend-heavy scene (R/P ~ 50 at 1080p)")
     ap.add_argument("--repeats", type=int, default=5, help="minimum number of timed regions of --steps steps")
     ap.add_argument("--min-seconds", type=float, default=2.0, help="minimum total time of the timed regions of a leg")
-    ap.add_argument("--mode", default="graph", choices=["graph", "streams"],
-                    help="our arm: graph = the step captured in a CUDA graph over the asynchronous forward (default); "
-                         "streams = eager launches, blocking forward, views pipelined over --streams CUDA streams")
+    ap.add_argument("--mode", default="batch", choices=["batch", "graph", "streams"],
+                    help="our arm: batch = the rank's views as ONE launch set (GaussianBatchRasterizer), the step "
+                         "captured in a CUDA graph (default); graph = one asynchronous forward/backward per view, the "
+                         "step captured in a CUDA graph; streams = eager launches, blocking forward, views pipelined "
+                         "over --streams CUDA streams")
+    ap.add_argument("--bwd-slices", type=int, default=4,
+                    help="batch mode, N > 1: slices of the batched backward whose gradient all-reduce overlaps the "
+                         "next slice (bags_view_parallel.SlicedGradientReducer)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-drop-in", action="store_true")
@@ -260,7 +265,8 @@ def main():
     vpg = args.views_per_gpu
     nviews = vpg * (world if ours else 1)
     my_views = list(range(rank, nviews, world)) if ours else list(range(nviews))
-    graph_mode = ours and args.mode == "graph"
+    batch_mode = ours and args.mode == "batch"
+    graph_mode = ours and args.mode in ("graph", "batch")
 
     # ---- scene: replicated Gaussians (seed 0, placed in front of camera 100), one camera per view (seed 100+v) -------
     cam0 = S.make_camera(W, H, seed=100)
@@ -397,6 +403,55 @@ def main():
             pipe.end()
         loss_dev[buf].copy_(torch.stack(losses).sum().reshape(1))
 
+    # ---- batch mode: the rank's views as one launch set ---------------------------------------------------------------
+    batch = {}
+    if batch_mode:
+        nb = len(views)
+        batch["up"] = [torch.stack([vw["up"][k] for vw in views]).contiguous() for k in range(3)]
+        batch["gt"] = [torch.empty(nb, 3, H, W, device=dev, dtype=torch.uint8) for _ in range(2)]
+        for k, vw in enumerate(views):            # the per-view ground-truth buffers become slices of the stacked ones
+            vw["gt_dev"] = [batch["gt"][0][k], batch["gt"][1][k]]
+        batch["m2d"] = torch.zeros(nb, P, 3, device=dev, requires_grad=True)
+        batch["m2dd"] = torch.zeros(nb, P, 3, device=dev, requires_grad=True)
+        batch["reducer"] = VP.SlicedGradientReducer(params) if (use_dist and not args.no_overlap) else None
+        settings = [mod.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=vw["cam"].tanfovx, tanfovy=vw["cam"].tanfovy, bg=bg,
+            scale_modifier=1.0, viewmatrix=vw["view"], projmatrix=vw["proj"], intrinsic=vw["intrinsic"], sh_degree=3,
+            campos=vw["campos"], prefiltered=False, debug=False, debug_iter=0) for vw in views]
+        red = batch["reducer"]
+        batch["rast"] = mod.GaussianBatchRasterizer(settings, capacity,
+                                                    backward_slices=args.bwd_slices if red is not None else 1,
+                                                    on_slice=red.on_slice if red is not None else None)
+
+    def render_batch():
+        return batch["rast"](means3D=params["means3D"], means2D=batch["m2d"], means2D_densify=batch["m2dd"],
+                             shift_factors=shift, opacities=params["opacities"], shs=params["shs"],
+                             scales=params["scales"], rotations=params["rotations"])
+
+    def clear_batch_grads():
+        clear_pose_grads()
+        if batch:
+            batch["m2d"].grad = batch["m2dd"].grad = None
+
+    def body_device_batch():
+        params.zero_grad()
+        with params.accumulating():
+            color, radii, depth, weights, _ = render_batch()
+            torch.autograd.backward([color, depth, weights], batch["up"])
+        if batch["reducer"] is not None:
+            batch["reducer"].finish()
+
+    def body_e2e_batch(buf):
+        params.zero_grad()
+        with params.accumulating():
+            color, radii, depth, weights, _ = render_batch()
+            # sum over the views of each view's mean L1 = (number of views) x the mean over the stacked images
+            loss = view_loss(color, batch["gt"][buf]) * float(len(views))
+            loss.backward()
+        if batch["reducer"] is not None:
+            batch["reducer"].finish()
+        loss_dev[buf].copy_(loss.detach().reshape(1))
+
     capi = None
     tuned = {}
     if ours:
@@ -407,7 +462,16 @@ def main():
             tuned[k] = int(v)
     launches_per_step = None
     cap_dev = cap_e2e = None
-    if graph_mode:
+    if batch_mode:
+        clear_batch_grads()
+        cap_dev = VP.CapturedStep(body_device_batch, dev, mod, None, forwards_per_step=1, reset=clear_batch_grads,
+                                  check=batch["rast"].check)
+        l0 = capi.lib().bags_launch_count()
+        body_device_batch()
+        launches_per_step = int(capi.lib().bags_launch_count() - l0)
+        torch.cuda.synchronize()
+        clear_batch_grads()
+    elif graph_mode:
         clear_pose_grads()
         cap_dev = VP.CapturedStep(body_device, dev, mod, capacity, forwards_per_step=len(views),
                                   reset=clear_pose_grads)
@@ -422,8 +486,12 @@ def main():
     overlap = None
     if use_dist:
         overlap = None if args.no_overlap else VP.GradientReducer(params)
+    if batch_mode and batch["reducer"] is not None:
+        overlap = batch["reducer"]
 
     def reduce_grads():
+        if batch_mode and batch["reducer"] is not None:
+            return          # exchanged slice by slice inside the (captured) backward
         if use_dist:
             if overlap is not None:
                 overlap.reduce()
@@ -599,7 +667,11 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        if graph_mode:
+        if batch_mode:
+            clear_batch_grads()
+            cap_e2e = [VP.CapturedStep(lambda b=b: body_e2e_batch(b), dev, mod, None, forwards_per_step=1,
+                                      reset=clear_batch_grads, check=batch["rast"].check) for b in range(2)]
+        elif graph_mode:
             clear_pose_grads()
             cap_e2e = [VP.CapturedStep(lambda b=b: body_e2e(b), dev, mod, capacity, forwards_per_step=len(views),
                                       reset=clear_pose_grads) for b in range(2)]
@@ -648,7 +720,11 @@ def main():
         capi.lib().bags_profile_enable(1)
         capi.profile_read()
         for _ in range(3):
-            body_device(pipe_serial)       # one stream: concurrent kernels would inflate each other's event times
+            if batch_mode:
+                clear_batch_grads()
+                body_device_batch()
+            else:
+                body_device(pipe_serial)   # one stream: concurrent kernels would inflate each other's event times
         torch.cuda.synchronize()
         stage_ms, stage_calls = capi.profile_read()
         capi.lib().bags_profile_enable(0)
@@ -690,10 +766,13 @@ def main():
         return 0
 
     line["implementation"] = {
-        "mode": ("CUDA graph of the step's enqueue (bags_view_parallel.CapturedStep) over the asynchronous forward "
-                 f"(binning capacity {capacity} tile instances), one launch per step") if graph_mode
+        "mode": (f"the rank's {len(views)} views as ONE launch set (GaussianBatchRasterizer: bags_rasterize_forward_batch"
+                 f" / _backward_batch_*, binning capacity {capacity} tile instances per view), the step's enqueue "
+                 "captured in a CUDA graph, one launch per step") if batch_mode
+        else ("CUDA graph of the step's enqueue (bags_view_parallel.CapturedStep) over the asynchronous forward "
+              f"(binning capacity {capacity} tile instances), one launch per step") if graph_mode
         else "eager launches, blocking forward",
-        "streams": pipe.depth, "view_assignment": assignment,
+        "streams": 1 if batch_mode else pipe.depth, "view_assignment": assignment,
         "grad_accumulation": "kernel adds into the flat gradient buffer (register_grad_sink)" if grad_sinks
         else "autograd (fresh gradient tensors + add)",
         "allreduce": (overlap.describe() if overlap is not None else "one all_reduce after the step") if use_dist
@@ -718,7 +797,7 @@ def main():
                    "tile_sort": ab["sort"], "ranges": ab["ranges"], "blend_fwd": ab["blend_fwd"],
                    "blend_bwd": ab["blend_bwd"], "preprocess_bwd": ab["preprocess_bwd"], "bwd_clear": 0}
     stages = {}
-    nviews_prof = max(stage_calls.get("preprocess", 0), 1)      # one preprocess per view; a stage may record twice
+    nviews_prof = 3 * len(views)                                # views rendered by the profiling pass above
     for k, tot in stage_ms.items():
         avg = tot / nviews_prof
         gbs = stage_bytes.get(k, 0) / (avg * 1e-3) / 1e9 if avg > 0 else 0.0

@@ -53,6 +53,22 @@ SIGNATURES = {
                                               _P, _P, _P, _P, _P, _P, _P, _P,
                                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                               ctypes.c_uint, c_int, _P]),   # + accumulate_mask before debug
+    "bags_rasterize_forward_batch": (c_int, [c_int, ALLOC_FN, _P, ALLOC_FN, _P, ALLOC_FN, _P, c_int, c_int, c_int,
+                                             _P, c_int, c_int, _P, _P, _P, _P, _P, c_float, _P, _P,
+                                             _P, _P, _P, _P,                         # view, proj, campos, shift: [B][..]
+                                             _P, _P, c_int,                          # tan_fovx, tan_fovy (host [B]), prefiltered
+                                             _P, _P, _P, _P, _P, _P,
+                                             c_int, _P, _P]),                        # capacity, counts out [B], stream
+    "bags_backward_batch_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "bags_rasterize_backward_batch_blend": (c_int, [c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P,
+                                                    _P]),
+    "bags_rasterize_backward_batch_gaussians": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int,
+                                                        _P, _P, _P, c_float, _P, _P,     # means3D, shs, scales, mod, rot, cov3D
+                                                        _P, _P, _P, _P, _P,              # view, proj, campos, tanx, tany
+                                                        _P, _P, _P,                      # radii, geom, scratch
+                                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,   # dense outputs
+                                                        _P, _P, _P, _P,                  # proj, view, campos, shift
+                                                        ctypes.c_uint, c_int, c_int, _P]),
     "bags_mark_visible": (c_int, [c_int, _P, _P, _P, _P, _P]),
     "bags_compute_relocation": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "bags_knn_scratch_bytes": (c_size_t, [c_int]),

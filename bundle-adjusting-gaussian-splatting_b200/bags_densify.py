@@ -57,7 +57,19 @@ def selection_masks(g, max_grad, min_opacity, extent, max_screen_size, N=2):
     return keep, clone, child, sel_split
 
 
-def densify_and_prune(g, max_grad, min_opacity, extent, max_screen_size, N=2):
+def densify_and_prune(g, max_grad, min_opacity, extent, max_screen_size, N=2, _timing=None):
+    """`_timing` (a dict, development only): filled with wall-clock milliseconds per phase, each closed by a device
+    synchronisation."""
+    import time
+
+    def _mark(name, _t=[None]):
+        if _timing is None:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if _t[0] is not None:
+            _timing[name] = round((now - _t[0]) * 1e3, 3)
+        _t[0] = now
     if max_grad <= 0:
         raise RuntimeError("bags_densify: max_grad must be positive (with a non-positive threshold the reference also "
                            "splits the rows it has just cloned)")
@@ -67,18 +79,24 @@ def densify_and_prune(g, max_grad, min_opacity, extent, max_screen_size, N=2):
     dev = xyz.device
     P = xyz.shape[0]
     with torch.no_grad(), torch.cuda.device(dev):
+        _mark("start")
         keep, clone, child, split = selection_masks(g, max_grad, min_opacity, extent, max_screen_size, N)
-        bits = torch.stack([keep, clone, child, split], dim=1).to(torch.int32)              # [P, 4]
-        incl = torch.cumsum(bits, dim=0, dtype=torch.int32)
-        plan = (incl - bits).contiguous()                                                   # exclusive scans
-        flags = (bits * torch.tensor([1, 2, 4, 8], dtype=torch.int32, device=dev)).sum(1).to(torch.uint8).contiguous()
-        kept, clones, children, parents = (incl[-1].tolist() if P > 0 else [0, 0, 0, 0])    # the one host sync
+        _mark("masks")
+        # four scans along the contiguous axis (a cumsum down the rows of a [P, 4] tensor is ~100x slower), then
+        # interleaved to the [P][4] records the kernel reads with one 16-byte load
+        bits = torch.stack([keep, clone, child, split], dim=0).to(torch.int32)              # [4, P]
+        incl = torch.cumsum(bits, dim=1, dtype=torch.int32)
+        plan = (incl - bits).t().contiguous()                                               # exclusive scans, [P, 4]
+        flags = (bits[0] | (bits[1] << 1) | (bits[2] << 2) | (bits[3] << 3)).to(torch.uint8).contiguous()
+        kept, clones, children, parents = (incl[:, -1].tolist() if P > 0 else [0, 0, 0, 0])  # the one host sync
+        _mark("scan")
         # same random draw as densify_and_split (:404-406)
         stds = g.get_scaling[split].repeat(N, 1)
         means = torch.zeros((stds.size(0), 3), device=dev)
         samples = torch.normal(mean=means, std=stds).contiguous() if parents > 0 else means
         P_out = kept + clones + N * children
         rotation = g._rotation.detach().contiguous()
+        _mark("samples")
 
         descs, news = [], []
         for group in g.optimizer.param_groups:
@@ -100,11 +118,13 @@ def densify_and_prune(g, max_grad, min_opacity, extent, max_screen_size, N=2):
                                             dv.data_ptr() if dv is not None else None, int(width),
                                             ROLE.get(group["name"], 0)))
             news.append((group, old, state, dst, dm, dv, (src, sm, sv)))
+        _mark("alloc")
         arr = (capi.DensifyTensor * len(descs))(*descs)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         rc = capi.lib().bags_densify_gather(P, N, plan.data_ptr(), flags.data_ptr(), kept, clones, children, parents,
                                             rotation.data_ptr(), samples.data_ptr(), len(descs), arr, stream)
         capi.check(rc, "bags_densify_gather")
+        _mark("gather")
 
         # hand the new tensors to the optimizer the way cat_tensors_to_optimizer / _prune_optimizer do (:315-373)
         for group, old, state, dst, dm, dv, _keepalive in news:
@@ -122,4 +142,5 @@ def densify_and_prune(g, max_grad, min_opacity, extent, max_screen_size, N=2):
         g.xyz_gradient_accum = torch.zeros((P_out, 1), device=dev)                          # :390-393 then :345-348
         g.denom = torch.zeros((P_out, 1), device=dev)
         g.max_radii2D = torch.zeros((P_out,), device=dev)
+        _mark("rebind")
     return {"kept": kept, "clones": clones, "children": N * children, "split_parents": parents, "rows": P_out}

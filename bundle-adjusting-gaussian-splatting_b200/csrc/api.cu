@@ -586,6 +586,240 @@ extern "C" int bags_rasterize_backward(
         dL_dviewmatrix, dL_dcampos, dL_dshift, 0u, debug, stream);
 }
 
+// ---- batched launch set (B views of the same Gaussians) -----------------------------------------------------------
+static int fill_fov(int B, int width, int height, const float* tan_fovx, const float* tan_fovy, ViewFov* fov) {
+    for (int v = 0; v < B; v++) {
+        fov->tan_fovx[v] = tan_fovx[v];
+        fov->tan_fovy[v] = tan_fovy[v];
+        fov->focal_y[v] = height / (2.0f * tan_fovy[v]);
+        fov->focal_x[v] = width / (2.0f * tan_fovx[v]);
+    }
+    for (int v = B; v < MAX_BATCH; v++) {
+        fov->tan_fovx[v] = fov->tan_fovy[v] = fov->focal_x[v] = fov->focal_y[v] = 0.f;
+    }
+    return 0;
+}
+
+extern "C" int bags_rasterize_forward_batch(
+    int B, bags_alloc_fn geom_alloc, void* geom_user, bags_alloc_fn binning_alloc, void* binning_user,
+    bags_alloc_fn image_alloc, void* image_user, int P, int D, int M, const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+    float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+    const float* projmatrix, const float* cam_pos, const float* shift_factors, const float* tan_fovx,
+    const float* tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha, int* radii,
+    float* mean2Dx, float* mean2Dy, int capacity, unsigned long long* num_rendered_out, void* stream) {
+    static_assert(MAX_BATCH == BAGS_MAX_BATCH, "header / kernel batch limits differ");
+    cudaStream_t st = (cudaStream_t)stream;
+    BAGS_REQUIRE(B >= 1 && B <= MAX_BATCH, "batch size out of range");
+    BAGS_REQUIRE(P >= 0 && width > 0 && height > 0, "negative P or empty image");
+    BAGS_REQUIRE(out_color && out_depth && out_alpha, "null output image");
+    BAGS_REQUIRE(geom_alloc && binning_alloc && image_alloc, "null allocation callback");
+    BAGS_REQUIRE(capacity >= 0 && capacity < (1 << 30), "capacity does not fit the 30-bit look-back words");
+    const size_t N = (size_t)width * height;
+    if (P == 0) {
+        BAGS_CUDA_OK(cudaMemsetAsync(out_color, 0, B * 3 * N * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(out_depth, 0, B * N * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(out_alpha, 0, B * N * sizeof(float), st));
+        if (num_rendered_out) BAGS_CUDA_OK(cudaMemsetAsync(num_rendered_out, 0, B * sizeof(unsigned long long), st));
+        return 0;
+    }
+    BAGS_REQUIRE(background && means3D && opacities && viewmatrix && projmatrix && cam_pos && shift_factors &&
+                     tan_fovx && tan_fovy, "null required input");
+    BAGS_REQUIRE(radii && mean2Dx && mean2Dy, "null per-Gaussian output");
+    BAGS_REQUIRE((shs != nullptr) != (colors_precomp != nullptr), "provide exactly one of shs / colors_precomp");
+    BAGS_REQUIRE((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr),
+                 "provide exactly one of scales+rotations / cov3D_precomp");
+    BAGS_REQUIRE(shs == nullptr || (M >= (D + 1) * (D + 1) && D >= 0 && D <= 3), "SH degree / coefficient count");
+    BAGS_REQUIRE(tiles_x(width) <= 65535 && tiles_y(height) <= 65535, "image too large for 16-bit tile coordinates");
+
+    ViewStride vs;
+    vs.geom = GeomState::bytes(P);
+    vs.bin = BinningState::bytes(capacity);
+    vs.img = ImageState::bytes(width, height);
+    char* geom_ptr = geom_alloc(B * vs.geom, geom_user);
+    char* img_ptr = image_alloc(B * vs.img, image_user);
+    char* bin_ptr = binning_alloc(B * vs.bin, binning_user);
+    if (!geom_ptr || !img_ptr || !bin_ptr) {
+        set_error("allocation callback returned NULL");
+        return BAGS_E_ALLOC;
+    }
+    BAGS_REQUIRE((((size_t)geom_ptr | (size_t)img_ptr | (size_t)bin_ptr) & 255) == 0,
+                 "batched state buffers must be 256-byte aligned");
+    GeomState g = GeomState::from(geom_ptr, P);
+    ImageState img = ImageState::from(img_ptr, width, height);
+    const int ntiles = tiles_x(width) * tiles_y(height);
+    const int npass = tile_sort_passes(ntiles);
+    BinningState b = BinningState::from(bin_ptr, capacity, npass);
+
+    ViewFov fov;
+    fill_fov(B, width, height, tan_fovx, tan_fovy, &fov);
+    FwdArgs a;
+    a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
+    a.background = background; a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp;
+    a.opacities = opacities; a.scales = scales; a.scale_modifier = scale_modifier; a.rotations = rotations;
+    a.cov3D_precomp = cov3D_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+    a.shift_factors = shift_factors; a.tan_fovx = tan_fovx[0]; a.tan_fovy = tan_fovy[0];
+    a.focal_x = fov.focal_x[0]; a.focal_y = fov.focal_y[0];
+    a.prefiltered = prefiltered;
+
+    int rc;
+    // counters + emit totals + depth-sort bookkeeping of every view: one strided memset
+    BAGS_CUDA_OK(cudaMemset2DAsync(g.counters, vs.geom, 0, ((char*)g.sort.ghist - (char*)g.counters) + g.sort.zero_bytes,
+                                   (size_t)B, st));
+    {
+        ProfScope ps(BAGS_STAGE_PREPROCESS, st);
+        rc = launch_preprocess_fwd(a, g, radii, mean2Dx, mean2Dy, st, B, &fov, vs.geom);
+    }
+    if (rc) return rc;
+    if (num_rendered_out)
+        BAGS_CUDA_OK(cudaMemcpy2DAsync(num_rendered_out, sizeof(unsigned long long), g.counters, vs.geom,
+                                       sizeof(unsigned long long), (size_t)B, cudaMemcpyDefault, st));
+    u32 *sorted_keys, *sorted_idx;
+    {
+        ProfScope ps(BAGS_STAGE_DEPTH_SORT, st);
+        rc = launch_sort_pairs(P, nullptr, g.key_a, g.idx_a, g.key_b, g.idx_b, 0, 32, g.sort, true, SORT_PREPARED, st,
+                               &sorted_keys, &sorted_idx, B, vs.geom, 0);
+    }
+    if (rc) return rc;
+    u32* offsets = (sorted_keys == g.key_a) ? g.key_b : g.key_a;
+    {
+        ProfScope ps(BAGS_STAGE_EMIT, st);
+        rc = launch_emit_scan(P, g, sorted_idx, offsets, st, B, vs);
+    }
+    if (rc) return rc;
+    const int R = capacity;
+    const unsigned long long* R_dev = g.counters;
+    if (R > 0) {
+        const int hist_passes = npass <= 2 ? npass : 0;
+        {
+            ProfScope ps(BAGS_STAGE_EMIT, st);
+            BAGS_CUDA_OK(cudaMemset2DAsync(b.sort.ghist, vs.bin, 0, b.sort.zero_bytes, (size_t)B, st));
+            rc = launch_emit_fill(P, R, R_dev, g, sorted_idx, offsets, b, tiles_x(width), hist_passes, st, B, vs);
+        }
+        if (rc) return rc;
+        u32 *fk, *fv;
+        {
+            ProfScope ps(BAGS_STAGE_TILE_SORT, st);
+            rc = launch_sort_pairs(R, R_dev, b.tile_buf[0], b.id_buf[0], b.tile_buf[1], b.id_buf[1], 0,
+                                   tile_sort_bits(ntiles), b.sort, false,
+                                   hist_passes > 0 ? SORT_HIST_DONE : SORT_PREPARED, st, &fk, &fv, B, vs.bin, vs.geom);
+        }
+        if (rc) return rc;
+        if (fv != b.point_list || fk != b.tile_sorted) {
+            set_error("internal: tile sort ping-pong parity mismatch");
+            return BAGS_E_INVALID;
+        }
+    }
+    {
+        ProfScope ps(BAGS_STAGE_RANGES, st);
+        rc = launch_ranges(R, R_dev, ntiles, b.tile_sorted, img.ranges, st, B, vs);
+    }
+    if (rc) return rc;
+    {
+        ProfScope ps(BAGS_STAGE_BLEND_FWD, st);
+        rc = launch_blend_fwd(width, height, g, b, img, background, out_color, out_depth, out_alpha, st, B, vs);
+    }
+    return rc;
+}
+
+static inline size_t gacc_view_bytes(int P) { return align_up((size_t)(P < 0 ? 0 : P) * GACC_STRIDE * sizeof(float)); }
+
+extern "C" size_t bags_backward_batch_scratch_bytes(int B, int P) {
+    if (B < 1) B = 1;
+    return (size_t)B * gacc_view_bytes(P) + align_up((size_t)B * POSE_ACC_DOUBLES * sizeof(double)) + 256;
+}
+
+extern "C" int bags_rasterize_backward_batch_blend(int B, int P, int R, const float* background, int width, int height,
+                                                   const char* geom_buffer, const char* binning_buffer,
+                                                   const char* image_buffer, const float* dL_dpix,
+                                                   const float* dL_dpix_depth, const float* dL_dalpha, char* scratch,
+                                                   void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    BAGS_REQUIRE(B >= 1 && B <= MAX_BATCH, "batch size out of range");
+    BAGS_REQUIRE(P >= 0 && R >= 0 && width > 0 && height > 0, "negative size");
+    BAGS_REQUIRE(scratch != nullptr, "null scratch");
+    if (P == 0) return 0;
+    BAGS_REQUIRE(background && geom_buffer && binning_buffer && image_buffer && dL_dpix, "null required input");
+    BAGS_REQUIRE((((size_t)geom_buffer | (size_t)binning_buffer | (size_t)image_buffer) & 255) == 0,
+                 "batched state buffers must be 256-byte aligned");
+    char* sp = (char*)align_up((size_t)scratch);
+    const size_t gstride = gacc_view_bytes(P);
+    {
+        ProfScope ps(BAGS_STAGE_BWD_CLEAR, st);
+        BAGS_CUDA_OK(cudaMemsetAsync(sp, 0, (size_t)B * gstride + (size_t)B * POSE_ACC_DOUBLES * sizeof(double), st));
+    }
+    if (R == 0) return 0;
+    ViewStride vs;
+    vs.geom = GeomState::bytes(P);
+    vs.bin = BinningState::bytes(R);
+    vs.img = ImageState::bytes(width, height);
+    GeomState g = GeomState::from(const_cast<char*>(geom_buffer), P);
+    const int ntiles = tiles_x(width) * tiles_y(height);
+    BinningState b = BinningState::from(const_cast<char*>(binning_buffer), R, tile_sort_passes(ntiles));
+    ImageState img = ImageState::from(const_cast<char*>(image_buffer), width, height);
+    ProfScope ps(BAGS_STAGE_BLEND_BWD, st);
+    return launch_blend_bwd(width, height, g, b, img, background, dL_dpix, dL_dpix_depth, dL_dalpha, (float*)sp, st, B,
+                            vs, gstride);
+}
+
+extern "C" int bags_rasterize_backward_batch_gaussians(
+    int B, int P, int D, int M, int width, int height, const float* means3D, const float* shs, const float* scales,
+    float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+    const float* projmatrix, const float* campos, const float* tan_fovx, const float* tan_fovy, const int* radii,
+    const char* geom_buffer, const char* scratch, float* dL_dmean2D, float* dL_dmean2D_densify, float* covariance,
+    float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+    float* dL_drot, float* dL_dprojmatrix, float* dL_dviewmatrix, float* dL_dcampos, float* dL_dshift,
+    unsigned accumulate_mask, int first, int count, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    BAGS_REQUIRE(B >= 1 && B <= MAX_BATCH, "batch size out of range");
+    BAGS_REQUIRE(P >= 0 && width > 0 && height > 0, "negative size");
+    BAGS_REQUIRE(first >= 0 && count >= 0 && (long long)first + count <= P, "slice outside [0, P)");
+    BAGS_REQUIRE((accumulate_mask & ~(BAGS_ACC_MEANS3D | BAGS_ACC_SH | BAGS_ACC_OPACITY | BAGS_ACC_SCALE |
+                                      BAGS_ACC_ROT)) == 0, "unknown bit in accumulate_mask");
+    BAGS_REQUIRE(scratch && dL_dprojmatrix && dL_dviewmatrix && dL_dcampos && dL_dshift, "null pose output/scratch");
+    if (P == 0) {
+        // .mean(0) of empty tensors, like the single-view backward
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dprojmatrix, 0xFF, (size_t)B * 16 * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dviewmatrix, 0xFF, (size_t)B * 16 * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dcampos, 0xFF, (size_t)B * 3 * sizeof(float), st));
+        BAGS_CUDA_OK(cudaMemsetAsync(dL_dshift, 0xFF, (size_t)B * 3 * sizeof(float), st));
+        return 0;
+    }
+    BAGS_REQUIRE(means3D && viewmatrix && projmatrix && campos && tan_fovx && tan_fovy && radii && geom_buffer,
+                 "null required input");
+    BAGS_REQUIRE(dL_dmean2D && dL_dmean2D_densify && dL_dopacity && dL_dmean3D && dL_dscale && dL_drot,
+                 "null dense output");
+    BAGS_REQUIRE(shs == nullptr || dL_dsh != nullptr, "null dL_dsh with SH input");
+    BAGS_REQUIRE((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr),
+                 "provide exactly one of scales+rotations / cov3D_precomp");
+    BAGS_REQUIRE(((size_t)geom_buffer & 255) == 0, "batched state buffers must be 256-byte aligned");
+    const char* sp = (const char*)align_up((size_t)scratch);
+    const size_t gstride = gacc_view_bytes(P);
+    const float* gacc = (const float*)sp;
+    double* pose_acc = (double*)(sp + (size_t)B * gstride);
+    ViewFov fov;
+    fill_fov(B, width, height, tan_fovx, tan_fovy, &fov);
+    BwdArgs a;
+    a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
+    a.means3D = means3D; a.shs = shs; a.colors_precomp = nullptr; a.scales = scales;
+    a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+    a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.campos = campos; a.tan_fovx = tan_fovx[0];
+    a.tan_fovy = tan_fovy[0]; a.focal_x = fov.focal_x[0]; a.focal_y = fov.focal_y[0];
+    a.radii = radii;
+    BwdOut po;
+    memset(&po, 0, sizeof(po));
+    po.dL_dprojmatrix = dL_dprojmatrix; po.dL_dviewmatrix = dL_dviewmatrix; po.dL_dcampos = dL_dcampos;
+    po.dL_dshift = dL_dshift;
+    BwdBatchOut o;
+    o.dL_dmean2D = dL_dmean2D; o.dL_dmean2D_densify = dL_dmean2D_densify; o.covariance = covariance;
+    o.dL_dopacity = dL_dopacity; o.dL_dcolor = dL_dcolor; o.dL_dmean3D = dL_dmean3D; o.dL_dcov3D = dL_dcov3D;
+    o.dL_dsh = dL_dsh; o.dL_dscale = dL_dscale; o.dL_drot = dL_drot;
+    GeomState g = GeomState::from(const_cast<char*>(geom_buffer), P);
+    ProfScope ps(BAGS_STAGE_PREPROCESS_BWD, st);
+    return launch_preprocess_bwd_batch(a, B, fov, g, GeomState::bytes(P), gacc, gstride, pose_acc, po, o,
+                                       accumulate_mask, first, count, first + count == P, st);
+}
+
 extern "C" int bags_unpack_state(int P, int R, int width, int height, const char* geom_buffer,
                                  const char* binning_buffer, const char* image_buffer, uint32_t* tiles_touched,
                                  uint32_t* depth_bits, float* xy, float* conic_opacity, float* rgb,

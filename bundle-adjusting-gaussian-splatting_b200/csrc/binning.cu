@@ -60,7 +60,11 @@ __device__ __forceinline__ int resolve_n(const int n_cap, const unsigned long lo
 // Histograms of every digit position in one read of the keys.
 __global__ void __launch_bounds__(512)
 sort_hist_kernel(const u32* __restrict__ keys, int n_cap, const unsigned long long* __restrict__ n_dev, int begin_bit,
-                 int end_bit, u32* __restrict__ ghist) {
+                 int end_bit, u32* __restrict__ ghist, const size_t data_stride, const size_t count_stride) {
+    // batched launch: blockIdx.y = view (strides are 0 for a single view)
+    keys = at_view(keys, data_stride, blockIdx.y);
+    ghist = at_view(ghist, data_stride, blockIdx.y);
+    if (n_dev != nullptr) n_dev = at_view(n_dev, count_stride, blockIdx.y);
     const int n = resolve_n(n_cap, n_dev);
     __shared__ u32 sh[SORT_MAX_PASSES][RADIX];
     for (int i = threadIdx.x; i < SORT_MAX_PASSES * RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
@@ -208,8 +212,18 @@ __global__ void __launch_bounds__(SORT_THREADS, 4)
 onesweep_pass_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, u32* __restrict__ keys_out,
                      u32* __restrict__ vals_out, int n_cap, const unsigned long long* __restrict__ n_dev, int shift,
                      int bits, const u32* __restrict__ ghist, u32* __restrict__ tile_counter,
-                     u32* __restrict__ status) {
+                     u32* __restrict__ status, const size_t data_stride, const size_t count_stride) {
     constexpr int TILE = ITEMS * SORT_THREADS;
+    if (data_stride != 0) {   // batched launch: blockIdx.y = view
+        keys_in = at_view(keys_in, data_stride, blockIdx.y);
+        vals_in = at_view(vals_in, data_stride, blockIdx.y);
+        keys_out = at_view(keys_out, data_stride, blockIdx.y);
+        vals_out = at_view(vals_out, data_stride, blockIdx.y);
+        ghist = at_view(ghist, data_stride, blockIdx.y);
+        tile_counter = at_view(tile_counter, data_stride, blockIdx.y);
+        status = at_view(status, data_stride, blockIdx.y);
+        if (n_dev != nullptr) n_dev = at_view(n_dev, count_stride, blockIdx.y);
+    }
     extern __shared__ u32 sort_smem[];
     u32* s_keys = sort_smem;                                             // [TILE] keys in locally sorted order
     u32* s_vals = s_keys + TILE;                                    // [TILE] their values
@@ -340,7 +354,9 @@ int sort_prepare(SortScratch& sc, cudaStream_t st) {
 // n_dev: see resolve_n (NULL = n is exact).  hist_mode: SORT_FRESH / SORT_PREPARED / SORT_HIST_DONE (common.cuh).
 int launch_sort_pairs(int n, const unsigned long long* n_dev, u32* keys_in, u32* vals_in, u32* keys_out,
                       u32* vals_out, int begin_bit, int end_bit, SortScratch& sc, bool iota_vals, int hist_mode,
-                      cudaStream_t st, u32** final_keys, u32** final_vals) {
+                      cudaStream_t st, u32** final_keys, u32** final_vals, int nviews, size_t data_stride,
+                      size_t count_stride) {
+    if (nviews <= 1) { nviews = 1; data_stride = 0; count_stride = 0; }
     const int npass = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
     if (npass < 1 || npass > SORT_MAX_PASSES) {
         set_error("sort: unsupported bit range [%d,%d)", begin_bit, end_bit);
@@ -352,17 +368,23 @@ int launch_sort_pairs(int n, const unsigned long long* n_dev, u32* keys_in, u32*
         return 0;
     }
     if (hist_mode == SORT_FRESH) {
+        if (nviews > 1) {
+            set_error("sort: a batched sort needs its bookkeeping zeroed by the caller");
+            return BAGS_E_INVALID;
+        }
         int rc = sort_prepare(sc, st);
         if (rc) return rc;
     }
     if (hist_mode != SORT_HIST_DONE) {
         int hist_blocks = min((n + 512 * 8 - 1) / (512 * 8), 148 * 4);
-        sort_hist_kernel<<<hist_blocks, 512, 0, st>>>(keys_in, n, n_dev, begin_bit, end_bit, sc.ghist);
+        sort_hist_kernel<<<dim3(hist_blocks, nviews), 512, 0, st>>>(keys_in, n, n_dev, begin_bit, end_bit, sc.ghist,
+                                                                     data_stride, count_stride);
         BAGS_LAUNCH_OK("sort_hist_kernel");
     }
     // Keys per CTA: 4096 when the pass runs in several waves (throughput bound), 2048 when even that leaves the GPU
     // under-filled -- a pass over 1 M keys is bounded by the latency of one CTA's instruction stream, which halves.
-    const bool small = g_sort_small_tiles && (n + SORT_TILE - 1) / SORT_TILE < 2 * 148;
+    // (the views of a batch are one launch: `nviews` times the CTAs)
+    const bool small = g_sort_small_tiles && (long long)nviews * ((n + SORT_TILE - 1) / SORT_TILE) < 2 * 148;
     const int tile_keys = small ? SORT_TILE_SMALL : SORT_TILE;
     const int ntiles = (n + tile_keys - 1) / tile_keys;
     u32 *ki = keys_in, *vi = vals_in, *ko = keys_out, *vo = vals_out;
@@ -385,8 +407,10 @@ int launch_sort_pairs(int n, const unsigned long long* n_dev, u32* keys_in, u32*
                                               (int)sort_smem_bytes(ITEMS)));                                       \
             attr_set[cur_dev & 63].store(1, std::memory_order_release);                                            \
         }                                                                                                          \
-        onesweep_pass_kernel<IOTA, LB, BYTE, ITEMS, HWM><<<ntiles, SORT_THREADS, sort_smem_bytes(ITEMS), st>>>(    \
-            ki, vi, ko, vo, n, n_dev, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status);               \
+        onesweep_pass_kernel<IOTA, LB, BYTE, ITEMS, HWM>                                                           \
+            <<<dim3(ntiles, nviews), SORT_THREADS, sort_smem_bytes(ITEMS), st>>>(                                  \
+                ki, vi, ko, vo, n, n_dev, sft, bits, sc.ghist + p * RADIX, sc.tile_counter + p, status,            \
+                data_stride, count_stride);                                                                        \
     } while (0)
 #define BAGS_PASS_I(IOTA, LB, BYTE)                                                                                \
     do {                                                                                                           \
@@ -438,7 +462,10 @@ __device__ __forceinline__ u32 emit_count_of(int i, int P, const u32* __restrict
 
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_count_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect,
-                  u32* __restrict__ tile_total) {
+                  u32* __restrict__ tile_total, const size_t geom_stride) {
+    sorted_idx = at_view(sorted_idx, geom_stride, blockIdx.y);
+    rect = at_view(rect, geom_stride, blockIdx.y);
+    tile_total = at_view(tile_total, geom_stride, blockIdx.y);
     __shared__ u32 s_wsum[EMIT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u32 v = emit_count_of(blockIdx.x * EMIT_THREADS + tid, P, sorted_idx, rect);
@@ -456,7 +483,11 @@ emit_count_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __re
 
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_scan_kernel(int P, const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect,
-                 const u32* __restrict__ tile_total, u32* __restrict__ offsets) {
+                 const u32* __restrict__ tile_total, u32* __restrict__ offsets, const size_t geom_stride) {
+    sorted_idx = at_view(sorted_idx, geom_stride, blockIdx.y);
+    rect = at_view(rect, geom_stride, blockIdx.y);
+    tile_total = at_view(tile_total, geom_stride, blockIdx.y);
+    offsets = at_view(offsets, geom_stride, blockIdx.y);
     __shared__ u32 s_wsum[EMIT_THREADS / 32];
     __shared__ u32 s_wbase[EMIT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -503,7 +534,17 @@ constexpr int EMIT_FILL_PAD = 2 * EMIT_FILL_SLOTS;                     // power-
 __global__ void __launch_bounds__(EMIT_FILL_THREADS)
 emit_fill_kernel(int P, int R_cap, const unsigned long long* __restrict__ R_dev, const u32* __restrict__ offsets,
                  const u32* __restrict__ sorted_idx, const ushort4* __restrict__ rect, int grid_x,
-                 u32* __restrict__ tile_out, u32* __restrict__ id_out, u32* __restrict__ ghist, int hist_passes) {
+                 u32* __restrict__ tile_out, u32* __restrict__ id_out, u32* __restrict__ ghist, int hist_passes,
+                 const ViewStride vs) {
+    if (vs.geom != 0) {   // batched launch: blockIdx.y = view
+        R_dev = at_view(R_dev, vs.geom, blockIdx.y);
+        offsets = at_view(offsets, vs.geom, blockIdx.y);
+        sorted_idx = at_view(sorted_idx, vs.geom, blockIdx.y);
+        rect = at_view(rect, vs.geom, blockIdx.y);
+        tile_out = at_view(tile_out, vs.bin, blockIdx.y);
+        id_out = at_view(id_out, vs.bin, blockIdx.y);
+        if (ghist != nullptr) ghist = at_view(ghist, vs.bin, blockIdx.y);
+    }
     __shared__ u32 s_off[EMIT_FILL_PAD];
     __shared__ u32 s_hist[2][RADIX];
     __shared__ int s_lo;
@@ -593,11 +634,14 @@ emit_fill_kernel(int P, int R_cap, const unsigned long long* __restrict__ R_dev,
     }
 }
 
-int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st) {
+int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st, int nviews,
+                     const ViewStride& vs) {
     const int blocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;
-    emit_count_kernel<<<blocks, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.emit_status);
+    const dim3 grid(blocks, nviews > 1 ? nviews : 1);
+    const size_t gs = nviews > 1 ? vs.geom : 0;
+    emit_count_kernel<<<grid, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.emit_status, gs);
     BAGS_LAUNCH_OK("emit_count_kernel");
-    emit_scan_kernel<<<blocks, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.emit_status, offsets);
+    emit_scan_kernel<<<grid, EMIT_THREADS, 0, st>>>(P, sorted_idx, g.rect, g.emit_status, offsets, gs);
     BAGS_LAUNCH_OK("emit_scan_kernel");
     return 0;
 }
@@ -605,11 +649,12 @@ int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offs
 // hist_passes: 1 or 2 -> the tile sort's digit histograms are accumulated into b.sort.ghist (sort_prepare() must have
 // run); 0 -> not (more than two 8-bit digits: the sort makes its own histogram pass).
 int launch_emit_fill(int P, int R, const unsigned long long* R_dev, const GeomState& g, const u32* sorted_idx,
-                     const u32* offsets, BinningState& b, int grid_x, int hist_passes, cudaStream_t st) {
+                     const u32* offsets, BinningState& b, int grid_x, int hist_passes, cudaStream_t st, int nviews,
+                     const ViewStride& vs) {
     const int blocks = (R + EMIT_FILL_SLOTS - 1) / EMIT_FILL_SLOTS;
-    emit_fill_kernel<<<blocks, EMIT_FILL_THREADS, 0, st>>>(P, R, R_dev, offsets, sorted_idx, g.rect, grid_x,
-                                                          b.tile_buf[0], b.id_buf[0],
-                                                          hist_passes > 0 ? b.sort.ghist : nullptr, hist_passes);
+    emit_fill_kernel<<<dim3(blocks, nviews > 1 ? nviews : 1), EMIT_FILL_THREADS, 0, st>>>(
+        P, R, R_dev, offsets, sorted_idx, g.rect, grid_x, b.tile_buf[0], b.id_buf[0],
+        hist_passes > 0 ? b.sort.ghist : nullptr, hist_passes, nviews > 1 ? vs : ViewStride());
     BAGS_LAUNCH_OK("emit_fill_kernel");
     return 0;
 }
@@ -621,7 +666,10 @@ int launch_emit_fill(int P, int R, const unsigned long long* R_dev, const GeomSt
 constexpr int RANGE_ITEMS = 4;
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(int R_cap, const unsigned long long* __restrict__ R_dev, const u32* __restrict__ tile_sorted,
-                   uint2* __restrict__ ranges) {
+                   uint2* __restrict__ ranges, const ViewStride vs) {
+    if (R_dev != nullptr) R_dev = at_view(R_dev, vs.geom, blockIdx.y);
+    tile_sorted = at_view(tile_sorted, vs.bin, blockIdx.y);
+    ranges = at_view(ranges, vs.img, blockIdx.y);
     const int R = resolve_n(R_cap, R_dev);
     // thread-striped over RANGE_ITEMS * 256 consecutive elements per CTA (coalesced loads)
     const int base = blockIdx.x * (256 * RANGE_ITEMS) + threadIdx.x;
@@ -644,11 +692,14 @@ tile_ranges_kernel(int R_cap, const unsigned long long* __restrict__ R_dev, cons
 }
 
 int launch_ranges(int R, const unsigned long long* R_dev, int ntiles, const u32* tile_sorted, uint2* ranges,
-                  cudaStream_t st) {
-    BAGS_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)ntiles * sizeof(uint2), st));
+                  cudaStream_t st, int nviews, const ViewStride& vs) {
+    if (nviews > 1)
+        BAGS_CUDA_OK(cudaMemset2DAsync(ranges, vs.img, 0, (size_t)ntiles * sizeof(uint2), (size_t)nviews, st));
+    else
+        BAGS_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)ntiles * sizeof(uint2), st));
     if (R > 0) {
-        tile_ranges_kernel<<<(R + 256 * RANGE_ITEMS - 1) / (256 * RANGE_ITEMS), 256, 0, st>>>(R, R_dev, tile_sorted,
-                                                                                            ranges);
+        tile_ranges_kernel<<<dim3((R + 256 * RANGE_ITEMS - 1) / (256 * RANGE_ITEMS), nviews > 1 ? nviews : 1), 256, 0,
+                             st>>>(R, R_dev, tile_sorted, ranges, nviews > 1 ? vs : ViewStride());
         BAGS_LAUNCH_OK("tile_ranges_kernel");
     }
     return 0;

@@ -176,9 +176,21 @@ __global__ void __launch_bounds__(256 / PPT)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float4* __restrict__ rec, float* __restrict__ final_T, u32* __restrict__ n_contrib,
                  const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_depth,
-                 float* __restrict__ out_alpha, const bool cull) {
+                 float* __restrict__ out_alpha, const bool cull, const ViewStride vs) {
     constexpr int NT = 256 / PPT;
     constexpr int NBUF = ASYNC ? 2 : 1;
+    if (blockIdx.z != 0) {   // batched launch: blockIdx.z = view, the images of the views are stacked
+        const unsigned v = blockIdx.z;
+        const size_t pl = (size_t)H * W * v;
+        ranges = at_view(ranges, vs.img, v);
+        final_T = at_view(final_T, vs.img, v);
+        n_contrib = at_view(n_contrib, vs.img, v);
+        point_list = at_view(point_list, vs.bin, v);
+        rec = at_view(rec, vs.geom, v);
+        out_color += 3 * pl;
+        out_depth += pl;
+        out_alpha += pl;
+    }
     __shared__ __align__(16) float4 sm_rec[NBUF][BATCH * 3];
     __shared__ u32 sm_cell[NBUF][BATCH];
     const u32 s_rec0 = smem_addr(sm_rec);
@@ -310,12 +322,13 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
 }
 
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
-                     float* out_color, float* out_depth, float* out_alpha, cudaStream_t st) {
-    dim3 grid(tiles_x(W), tiles_y(H), 1);
+                     float* out_color, float* out_depth, float* out_alpha, cudaStream_t st, int nviews,
+                     const ViewStride& vs) {
+    dim3 grid(tiles_x(W), tiles_y(H), nviews > 1 ? nviews : 1);
 #define BAGS_FWD(PPT, ASYNC)                                                                                     \
     blend_fwd_kernel<PPT, ASYNC><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, g.rec, img.final_T, \
                                                             img.n_contrib, bg, out_color, out_depth, out_alpha, \
-                                                            g_cull != 0)
+                                                            g_cull != 0, vs)
     if (g_staging) {
         if (g_fwd_ppt == 4) BAGS_FWD(4, true);
         else if (g_fwd_ppt == 2) BAGS_FWD(2, true);
@@ -389,9 +402,23 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                  const float* __restrict__ bg_color, const float4* __restrict__ rec,
                  const float* __restrict__ final_Ts, const u32* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
-                 const float* __restrict__ dL_dalphas, float* __restrict__ gacc, const bool cull) {
+                 const float* __restrict__ dL_dalphas, float* __restrict__ gacc, const bool cull, const ViewStride vs,
+                 const size_t gacc_stride) {
     constexpr int NT = 256 / PPT;
     constexpr int NW = NT / 32;
+    if (blockIdx.z != 0) {   // batched launch: blockIdx.z = view
+        const unsigned v = blockIdx.z;
+        const size_t pl = (size_t)H * W * v;
+        ranges = at_view(ranges, vs.img, v);
+        final_Ts = at_view(final_Ts, vs.img, v);
+        n_contrib = at_view(n_contrib, vs.img, v);
+        point_list = at_view(point_list, vs.bin, v);
+        rec = at_view(rec, vs.geom, v);
+        dL_dpixels += 3 * pl;
+        if (dL_dpixel_depths) dL_dpixel_depths += pl;
+        if (dL_dalphas) dL_dalphas += pl;
+        gacc = at_view(gacc, gacc_stride, v);
+    }
     constexpr int NBUF = ASYNC ? 2 : 1;
     __shared__ __align__(16) float4 sm_rec[NBUF][BATCH * 3];
     __shared__ u32 sm_cell[NBUF][BATCH];
@@ -585,12 +612,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
 
 int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, const ImageState& img, const float* bg,
                      const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalpha, float* gacc,
-                     cudaStream_t st) {
-    dim3 grid(tiles_x(W), tiles_y(H), 1);
+                     cudaStream_t st, int nviews, const ViewStride& vs, size_t gacc_stride) {
+    dim3 grid(tiles_x(W), tiles_y(H), nviews > 1 ? nviews : 1);
 #define BAGS_BWD(PPT, ASYNC)                                                                                     \
     blend_bwd_kernel<PPT, ASYNC><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec,          \
                                                             img.final_T, img.n_contrib, dL_dpix, dL_dpix_depth, \
-                                                            dL_dalpha, gacc, g_cull != 0)
+                                                            dL_dalpha, gacc, g_cull != 0, vs, gacc_stride)
     if (g_staging) {
         if (g_bwd_ppt == 4) BAGS_BWD(4, true);
         else if (g_bwd_ppt == 2) BAGS_BWD(2, true);

@@ -138,6 +138,34 @@ struct ImageState {
     static ImageState from(char* p, int width, int height);
 };
 
+// ---- batched launches (bags_rasterize_forward_batch / _backward_batch) ---------------------------------------------
+// B views of the same Gaussians are one launch set: every per-view kernel gets the view as blockIdx.y (binning) or
+// blockIdx.z (blend), and the views' private states are B consecutive copies of the single-view layouts, so view v's
+// arrays sit `v * stride` bytes behind view 0's.  All strides are 0 for a single view.
+constexpr int MAX_BATCH = 8;
+struct ViewStride {
+    size_t geom = 0, bin = 0, img = 0;
+};
+#ifdef __CUDACC__
+template <typename T>
+__device__ __forceinline__ T* at_view(T* p, const size_t stride_bytes, const unsigned view) {
+    return reinterpret_cast<T*>(reinterpret_cast<size_t>(p) + stride_bytes * view);
+}
+#endif
+// per-view projection constants of a batch (kernel parameter, by value)
+struct ViewFov {
+    float tan_fovx[MAX_BATCH], tan_fovy[MAX_BATCH], focal_x[MAX_BATCH], focal_y[MAX_BATCH];
+};
+#ifdef __CUDACC__
+// Kernel parameters can only be indexed with compile-time constants without a local-memory copy: thread v of the CTA
+// moves view v's constants to shared memory ({tan_fovx, tan_fovy, focal_x, focal_y}).
+__device__ __forceinline__ void fov_to_shared(const ViewFov& fov, float4* s_fov) {
+#pragma unroll
+    for (int v = 0; v < MAX_BATCH; v++)
+        if (threadIdx.x == v) s_fov[v] = make_float4(fov.tan_fovx[v], fov.tan_fovy[v], fov.focal_x[v], fov.focal_y[v]);
+}
+#endif
+
 inline int tiles_x(int w) { return (w + TILE_X - 1) / TILE_X; }
 inline int tiles_y(int h) { return (h + TILE_Y - 1) / TILE_Y; }
 
@@ -162,7 +190,7 @@ struct FwdArgs {
 };
 
 int launch_preprocess_fwd(const FwdArgs& a, GeomState& g, int* radii, float* mean2Dx, float* mean2Dy,
-                          cudaStream_t st);
+                          cudaStream_t st, int nviews = 1, const ViewFov* fov = nullptr, size_t geom_stride = 0);
 int launch_unpack(int P, int R, int W, int H, const GeomState& g, const BinningState& b, const ImageState& img,
                   u32* tiles_touched, u32* depth_bits, float* xy, float* conic_opacity, float* rgb, u32* point_list,
                   u64* point_list_keys, u32* ranges, u32* n_contrib, float* final_T, cudaStream_t st);
@@ -174,21 +202,26 @@ enum { SORT_FRESH = 0, SORT_PREPARED = 1, SORT_HIST_DONE = 2 };
 int sort_prepare(SortScratch& sc, cudaStream_t st);
 int launch_sort_pairs(int n, const unsigned long long* n_dev, u32* keys_in, u32* vals_in, u32* keys_out,
                       u32* vals_out, int begin_bit, int end_bit, SortScratch& sc, bool iota_vals, int hist_mode,
-                      cudaStream_t st, u32** final_keys, u32** final_vals);
-int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st);
+                      cudaStream_t st, u32** final_keys, u32** final_vals, int nviews = 1, size_t data_stride = 0,
+                      size_t count_stride = 0);
+// nviews > 1: one launch for the views of a batch (pointers are view 0's; see ViewStride)
+int launch_emit_scan(int P, const GeomState& g, const u32* sorted_idx, u32* offsets, cudaStream_t st, int nviews = 1,
+                     const ViewStride& vs = ViewStride());
 int launch_emit_fill(int P, int R, const unsigned long long* R_dev, const GeomState& g, const u32* sorted_idx,
-                     const u32* offsets, BinningState& b, int grid_x, int hist_passes, cudaStream_t st);
+                     const u32* offsets, BinningState& b, int grid_x, int hist_passes, cudaStream_t st,
+                     int nviews = 1, const ViewStride& vs = ViewStride());
 int set_sort_lookback(int value);
 int set_sort_small_tiles(int value);
 int set_sort_hwmatch(int value);
 int set_pbwd_min_blocks(int value);
 int launch_ranges(int R, const unsigned long long* R_dev, int ntiles, const u32* tile_sorted, uint2* ranges,
-                  cudaStream_t st);
+                  cudaStream_t st, int nviews = 1, const ViewStride& vs = ViewStride());
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
-                     float* out_color, float* out_depth, float* out_alpha, cudaStream_t st);
+                     float* out_color, float* out_depth, float* out_alpha, cudaStream_t st, int nviews = 1,
+                     const ViewStride& vs = ViewStride());
 int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, const ImageState& img, const float* bg,
                      const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalpha, float* gacc,
-                     cudaStream_t st);
+                     cudaStream_t st, int nviews = 1, const ViewStride& vs = ViewStride(), size_t gacc_stride = 0);
 
 struct BwdArgs {
     int P, D, M, W, H;
@@ -224,6 +257,25 @@ struct BwdOut {
 // gacc: [P][16] accumulated by blend_bwd; pose_acc: [32] doubles (sums + winner), zeroed by the caller.
 int launch_preprocess_bwd(const BwdArgs& a, const GeomState& g, const float* gacc, double* pose_acc,
                           const BwdOut& o, unsigned accumulate_mask, cudaStream_t st);
+
+constexpr int POSE_ACC_DOUBLES = 32;   // pose_acc doubles per view
+// outputs of the batched backward preprocess (see preprocess_bwd.cu)
+struct BwdBatchOut {
+    float* dL_dmean2D;          // [B][P][3]
+    float* dL_dmean2D_densify;  // [B][P][3]
+    float* covariance;          // [B][P] or NULL
+    float* dL_dopacity;         // [P]        summed over the views (as are all the following)
+    float* dL_dcolor;           // [P][3] or NULL
+    float* dL_dmean3D;          // [P][3]
+    float* dL_dcov3D;           // [P][6] or NULL
+    float* dL_dsh;              // [P][M][3] or NULL
+    float* dL_dscale;           // [P][3]
+    float* dL_drot;             // [P][4]
+};
+int launch_preprocess_bwd_batch(const BwdArgs& a, int B, const ViewFov& fov, const GeomState& g, size_t geom_stride,
+                                const float* gacc, size_t gacc_stride, double* pose_acc, const BwdOut& po,
+                                const BwdBatchOut& o, unsigned accumulate_mask, int first, int count, bool finalize,
+                                cudaStream_t st);
 
 constexpr int GACC_STRIDE = 16;
 // gacc record layout (floats)

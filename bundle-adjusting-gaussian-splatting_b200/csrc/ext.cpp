@@ -241,6 +241,146 @@ BwdTuple rasterize_gaussians_backward(
                            pose.slice(0, 16, 32), pose.slice(0, 35, 38), covariance);
 }
 
+// ---- B views of the same Gaussians as one launch set (bags_rasterize_forward_batch / _backward_batch_*) -----------
+// viewmatrix / projmatrix: (B, 4, 4); campos / shift_factors: (B, 3); tan_fovx / tan_fovy: B floats.  Returns
+// (color (B,3,H,W), depth (B,1,H,W), alpha (B,1,H,W), radii (B,P), geom, binning, image buffers, means2Dx, means2Dy (B,P,1)).
+using FwdBatchTuple = std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+                                 torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
+FwdBatchTuple rasterize_gaussians_batch(const torch::Tensor& background_, const torch::Tensor& means3D_,
+                                        const torch::Tensor& shift_factors_, const torch::Tensor& colors_,
+                                        const torch::Tensor& opacity_, const torch::Tensor& scales_,
+                                        const torch::Tensor& rotations_, const float scale_modifier,
+                                        const torch::Tensor& cov3D_precomp_, const torch::Tensor& viewmatrix_,
+                                        const torch::Tensor& projmatrix_, const std::vector<float>& tan_fovx,
+                                        const std::vector<float>& tan_fovy, const int image_height,
+                                        const int image_width, const torch::Tensor& sh_, const int degree,
+                                        const torch::Tensor& campos_, const bool prefiltered, const int64_t capacity,
+                                        const torch::Tensor& count_out) {
+    if (means3D_.ndimension() != 2 || means3D_.size(1) != 3) AT_ERROR("means3D must have dimensions (num_points, 3)");
+    TORCH_CHECK(means3D_.is_cuda(), "bags_b200: means3D must be a CUDA tensor (there is no CPU path)");
+    const torch::Device dev = means3D_.device();
+    c10::cuda::CUDAGuard guard(dev);
+    const int P = (int)means3D_.size(0);
+    const int H = image_height, W = image_width;
+    const int64_t B = (int64_t)tan_fovx.size();
+    TORCH_CHECK(B >= 1 && B <= BAGS_MAX_BATCH, "bags_b200: a batch holds 1..", BAGS_MAX_BATCH, " views, got ", B);
+    TORCH_CHECK((int64_t)tan_fovy.size() == B && viewmatrix_.numel() == 16 * B && projmatrix_.numel() == 16 * B &&
+                    campos_.numel() == 3 * B && shift_factors_.numel() == 3 * B,
+                "bags_b200: per-view inputs must be stacked: viewmatrix/projmatrix (B,4,4), campos/shift_factors (B,3)");
+    TORCH_CHECK(capacity >= 0, "capacity must be >= 0");
+
+    const torch::Tensor means3D = f32c(means3D_, dev), background = f32c(background_, dev),
+                        shift_factors = f32c(shift_factors_, dev), colors = f32c(colors_, dev),
+                        opacity = f32c(opacity_, dev), scales = f32c(scales_, dev), rotations = f32c(rotations_, dev),
+                        cov3D_precomp = f32c(cov3D_precomp_, dev), viewmatrix = f32c(viewmatrix_, dev),
+                        projmatrix = f32c(projmatrix_, dev), sh = f32c(sh_, dev), campos = f32c(campos_, dev);
+    const auto f32 = torch::TensorOptions().dtype(torch::kFloat32).device(dev);
+    torch::Tensor out_color = torch::empty({B, NUM_CHANNELS, H, W}, f32);
+    torch::Tensor out_depth = torch::empty({B, 1, H, W}, f32);
+    torch::Tensor out_alpha = torch::empty({B, 1, H, W}, f32);
+    torch::Tensor radii = torch::empty({B, P}, f32.dtype(torch::kInt32));
+    torch::Tensor means2Dx = torch::empty({B, P, 1}, f32);
+    torch::Tensor means2Dy = torch::empty({B, P, 1}, f32);
+    Resizable geom(dev), binning(dev), img(dev);
+    const int M = (sh.defined() && sh.numel() != 0) ? (int)sh.size(1) : 0;
+    unsigned long long* cnt = nullptr;
+    if (count_out.defined() && count_out.numel() > 0) {
+        TORCH_CHECK(count_out.scalar_type() == torch::kInt64 && count_out.is_contiguous() && count_out.numel() >= B,
+                    "count_out must be a contiguous int64 tensor with one element per view");
+        TORCH_CHECK(count_out.is_cuda() || count_out.is_pinned(), "count_out must be CUDA or pinned host memory");
+        cnt = reinterpret_cast<unsigned long long*>(count_out.data_ptr());
+    }
+    const int rc = bags_rasterize_forward_batch(
+        (int)B, Resizable::alloc, &geom, Resizable::alloc, &binning, Resizable::alloc, &img, P, degree, M,
+        ptr(background), W, H, ptr(means3D), ptr(sh), ptr(colors), ptr(opacity), ptr(scales), scale_modifier,
+        ptr(rotations), ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix), ptr(campos), ptr(shift_factors),
+        tan_fovx.data(), tan_fovy.data(), prefiltered ? 1 : 0, ptr(out_color), ptr(out_depth), ptr(out_alpha),
+        ptr<int>(radii), ptr(means2Dx), ptr(means2Dy), (int)capacity, cnt, current_stream(dev));
+    check(rc, "bags_rasterize_forward_batch");
+    return std::make_tuple(out_color, out_depth, out_alpha, radii, geom.t, binning.t, img.t, means2Dx, means2Dy);
+}
+
+// Step 1 of the batched backward: blend backward of all views.  Returns the scratch buffer step 2 reads.
+torch::Tensor rasterize_gaussians_backward_batch_blend(const torch::Tensor& background_, const int64_t P,
+                                                       const int64_t R, const torch::Tensor& dL_dout_color_,
+                                                       const c10::optional<torch::Tensor>& dL_dout_depth_,
+                                                       const c10::optional<torch::Tensor>& dL_dout_alpha_,
+                                                       const torch::Tensor& geomBuffer,
+                                                       const torch::Tensor& binningBuffer,
+                                                       const torch::Tensor& imageBuffer) {
+    const torch::Device dev = geomBuffer.device();
+    TORCH_CHECK(geomBuffer.is_cuda(), "bags_b200: CUDA tensors only (there is no CPU path)");
+    c10::cuda::CUDAGuard guard(dev);
+    TORCH_CHECK(dL_dout_color_.dim() == 4 && dL_dout_color_.size(1) == NUM_CHANNELS,
+                "dL_dout_color must have dimensions (B, 3, H, W)");
+    const int B = (int)dL_dout_color_.size(0), H = (int)dL_dout_color_.size(2), W = (int)dL_dout_color_.size(3);
+    const torch::Tensor background = f32c(background_, dev), dL_dout_color = f32c(dL_dout_color_, dev);
+    const torch::Tensor dL_dout_depth = dL_dout_depth_.has_value() ? f32c(*dL_dout_depth_, dev) : torch::Tensor();
+    const torch::Tensor dL_dout_alpha = dL_dout_alpha_.has_value() ? f32c(*dL_dout_alpha_, dev) : torch::Tensor();
+    torch::Tensor scratch = torch::empty({(int64_t)bags_backward_batch_scratch_bytes(B, (int)P)},
+                                         torch::TensorOptions().dtype(torch::kUInt8).device(dev));
+    check(bags_rasterize_backward_batch_blend(B, (int)P, (int)R, ptr(background), W, H, ptr<char>(geomBuffer),
+                                              ptr<char>(binningBuffer), ptr<char>(imageBuffer), ptr(dL_dout_color),
+                                              ptr(dL_dout_depth), ptr(dL_dout_alpha), ptr<char>(scratch),
+                                              current_stream(dev)),
+          "bags_rasterize_backward_batch_blend");
+    return scratch;
+}
+
+// Step 2: Gaussians [first, first + count) of all views, into caller-provided tensors (so that consecutive slices fill
+// the same tensors): per view dL_dmeans2D / dL_dmeans2D_densify (B,P,3), pose (38 B floats) = proj (B,16) | view (B,16) |
+// campos (B,3) | shift (B,3); summed over the views dL_dmeans3D (P,3), dL_dopacity (P,1), dL_dsh (P,M,3), dL_dscales (P,3), dL_drotations
+// (P,4), optional dL_dcolors (P,3), dL_dcov3D (P,6), covariance (B,P,1).  acc_mask: BAGS_ACC_* bits of the summed outputs
+// that are gradient sinks (added onto instead of written).
+void rasterize_gaussians_backward_batch_gaussians(
+    const torch::Tensor& means3D_, const torch::Tensor& radii_, const torch::Tensor& scales_,
+    const torch::Tensor& rotations_, const float scale_modifier, const torch::Tensor& cov3D_precomp_,
+    const torch::Tensor& viewmatrix_, const torch::Tensor& projmatrix_, const std::vector<float>& tan_fovx,
+    const std::vector<float>& tan_fovy, const int image_height, const int image_width, const torch::Tensor& sh_,
+    const int degree, const torch::Tensor& campos_, const torch::Tensor& geomBuffer, const torch::Tensor& scratch,
+    torch::Tensor dL_dmeans2D, torch::Tensor dL_dmeans2D_densify, torch::Tensor dL_dopacity,
+    torch::Tensor dL_dmeans3D, torch::Tensor dL_dsh, torch::Tensor dL_dscales, torch::Tensor dL_drotations,
+    torch::Tensor pose, const c10::optional<torch::Tensor>& dL_dcolors, const c10::optional<torch::Tensor>& dL_dcov3D,
+    const c10::optional<torch::Tensor>& covariance, const int64_t acc_mask, const int64_t first,
+    const int64_t count) {
+    const torch::Device dev = means3D_.device();
+    TORCH_CHECK(means3D_.is_cuda(), "bags_b200: means3D must be a CUDA tensor (there is no CPU path)");
+    c10::cuda::CUDAGuard guard(dev);
+    const int P = (int)means3D_.size(0);
+    const int64_t B = (int64_t)tan_fovx.size();
+    const torch::Tensor means3D = f32c(means3D_, dev), scales = f32c(scales_, dev), rotations = f32c(rotations_, dev),
+                        cov3D_precomp = f32c(cov3D_precomp_, dev), viewmatrix = f32c(viewmatrix_, dev),
+                        projmatrix = f32c(projmatrix_, dev), sh = f32c(sh_, dev), campos = f32c(campos_, dev);
+    const torch::Tensor radii = radii_.contiguous();
+    const int M = (sh.defined() && sh.numel() != 0) ? (int)sh.size(1) : 0;
+    auto need = [&](const torch::Tensor& t, int64_t numel, const char* name) {
+        TORCH_CHECK(t.defined() && t.is_cuda() && t.device() == dev && t.scalar_type() == torch::kFloat32 &&
+                        t.is_contiguous() && t.numel() == numel,
+                    "bags_b200: output ", name, " must be a contiguous fp32 CUDA tensor with ", numel, " elements");
+    };
+    need(dL_dmeans2D, B * P * 3, "dL_dmeans2D");
+    need(dL_dmeans2D_densify, B * P * 3, "dL_dmeans2D_densify");
+    need(dL_dopacity, P, "dL_dopacity");
+    need(dL_dmeans3D, (int64_t)P * 3, "dL_dmeans3D");
+    if (M > 0) need(dL_dsh, (int64_t)P * M * 3, "dL_dsh");
+    need(dL_dscales, (int64_t)P * 3, "dL_dscales");
+    need(dL_drotations, (int64_t)P * 4, "dL_drotations");
+    need(pose, B * 38, "pose");
+    float* col = nullptr; float* cov3 = nullptr; float* covar = nullptr;
+    if (dL_dcolors.has_value() && dL_dcolors->defined()) { need(*dL_dcolors, (int64_t)P * 3, "dL_dcolors"); col = ptr(*dL_dcolors); }
+    if (dL_dcov3D.has_value() && dL_dcov3D->defined()) { need(*dL_dcov3D, (int64_t)P * 6, "dL_dcov3D"); cov3 = ptr(*dL_dcov3D); }
+    if (covariance.has_value() && covariance->defined()) { need(*covariance, B * P, "covariance"); covar = ptr(*covariance); }
+    float* pp = ptr(pose);
+    check(bags_rasterize_backward_batch_gaussians(
+              (int)B, P, degree, M, image_width, image_height, ptr(means3D), ptr(sh), ptr(scales), scale_modifier,
+              ptr(rotations), ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix), ptr(campos), tan_fovx.data(),
+              tan_fovy.data(), ptr<int>(radii), ptr<char>(geomBuffer), ptr<char>(scratch), ptr(dL_dmeans2D),
+              ptr(dL_dmeans2D_densify), covar, ptr(dL_dopacity), col, ptr(dL_dmeans3D), cov3, ptr(dL_dsh),
+              ptr(dL_dscales), ptr(dL_drotations), pp, pp + 16 * B, pp + 32 * B, pp + 35 * B, (unsigned)acc_mask,
+              (int)first, (int)count, current_stream(dev)),
+          "bags_rasterize_backward_batch_gaussians");
+}
+
 // markVisible, rasterize_points.cu:278-297
 torch::Tensor mark_visible(const torch::Tensor& means3D_, const torch::Tensor& viewmatrix_,
                            const torch::Tensor& projmatrix_) {
@@ -333,6 +473,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("compute_relocation", &compute_relocation, py::call_guard<py::gil_scoped_release>());
     m.def("rasterize_gaussians_async", &rasterize_gaussians_async, py::call_guard<py::gil_scoped_release>());
     m.def("unpack_state", &unpack_state);
+    m.def("rasterize_gaussians_batch", &rasterize_gaussians_batch, py::call_guard<py::gil_scoped_release>());
+    m.def("rasterize_gaussians_backward_batch_blend", &rasterize_gaussians_backward_batch_blend,
+          py::call_guard<py::gil_scoped_release>());
+    m.def("rasterize_gaussians_backward_batch_gaussians", &rasterize_gaussians_backward_batch_gaussians,
+          py::call_guard<py::gil_scoped_release>());
+    m.attr("MAX_BATCH") = (int)BAGS_MAX_BATCH;
     m.attr("ACC_MEANS3D") = (int)BAGS_ACC_MEANS3D;
     m.attr("ACC_SH") = (int)BAGS_ACC_SH;
     m.attr("ACC_OPACITY") = (int)BAGS_ACC_OPACITY;

@@ -49,36 +49,69 @@ struct CamConst {
     float shift[3];
 };
 
+// One launch serves B views of the same Gaussians (B = 1: the single-view forward).  The view-independent part of a
+// Gaussian -- mean, scale, rotation -> 3D covariance, and its SH row in the warp's shared-memory tile -- is fetched and
+// computed once and used by every view; the per-view outputs go to B stacked copies of the single-view arrays
+// (`geom_stride` bytes apart inside the private state, P elements apart for radii / mean2Dx / mean2Dy).  The per-view
+// arithmetic is the same code whatever B is, so a batched view is bit-identical to the same view rendered alone.
 template <bool HAS_SH, bool HAS_COV>
-__global__ void __launch_bounds__(PRE_THREADS)
+__global__ void __launch_bounds__(PRE_THREADS, 8)
 preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
                       float scale_modifier, const float* __restrict__ rotations, const float* __restrict__ opacities,
                       const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
                       const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
                       const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
-                      const float* __restrict__ shift_factors, int W, int H, float tan_fovx, float tan_fovy,
-                      float focal_x, float focal_y, int grid_x, int grid_y, int prefiltered,
+                      const float* __restrict__ shift_factors, int W, int H, const __grid_constant__ ViewFov fov, const int B,
+                      int grid_x, int grid_y, int prefiltered,
                       int* __restrict__ radii, float* __restrict__ mean2Dx, float* __restrict__ mean2Dy,
-                      float4* __restrict__ rec, u32* __restrict__ depth_key, ushort4* __restrict__ rect_out,
-                      unsigned long long* __restrict__ total_tiles, int sh_vec4) {
+                      float4* __restrict__ rec0, u32* __restrict__ depth_key0, ushort4* __restrict__ rect_out0,
+                      unsigned long long* __restrict__ total_tiles, const size_t geom_stride, int sh_vec4) {
     extern __shared__ float sh_tiles[];      // [PRE_WARPS][32][sh_stride(M)], only used when HAS_SH
-    __shared__ CamConst cam;
-    __shared__ float c2w[4][4];
-    __shared__ u32 warp_sums[PRE_THREADS / 32];
+    __shared__ CamConst cams[MAX_BATCH];
+    __shared__ float c2ws[MAX_BATCH][4][4];
+    __shared__ u32 warp_sums[MAX_BATCH][PRE_THREADS / 32];
+    __shared__ float4 s_fov[MAX_BATCH];
 
-    if (threadIdx.x < 16) {
-        cam.view[threadIdx.x] = viewmatrix[threadIdx.x];
-        cam.proj[threadIdx.x] = projmatrix[threadIdx.x];
+    fov_to_shared(fov, s_fov);
+    for (int t = threadIdx.x; t < 16 * B; t += PRE_THREADS) {
+        cams[t >> 4].view[t & 15] = viewmatrix[t];
+        cams[t >> 4].proj[t & 15] = projmatrix[t];
     }
-    if (threadIdx.x < 3) {
-        cam.campos[threadIdx.x] = cam_pos[threadIdx.x];
-        cam.shift[threadIdx.x] = shift_factors[threadIdx.x];
+    if (threadIdx.x < 3 * B) {
+        cams[threadIdx.x / 3].campos[threadIdx.x % 3] = cam_pos[threadIdx.x];
+        cams[threadIdx.x / 3].shift[threadIdx.x % 3] = shift_factors[threadIdx.x];
     }
-    if (HAS_SH && threadIdx.x == 32) inverse_w2c(viewmatrix, c2w);
+    if (HAS_SH && threadIdx.x >= 32 && threadIdx.x < 32 + B)
+        inverse_w2c(viewmatrix + 16 * (threadIdx.x - 32), c2ws[threadIdx.x - 32]);
     __syncthreads();
 
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- view-independent inputs: fetched together (one memory round trip on the critical path of every warp) -----
+    // (the 3D covariance does not depend on the view: evaluated once, also for the ~5% of rows every view culls)
+    float3 p_orig = {0.f, 0.f, 0.f};
+    float cov6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (idx < P) {
+        p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+        if (HAS_COV) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * idx + k];
+        } else {
+            const float sc0 = scales[3 * idx], sc1 = scales[3 * idx + 1], sc2 = scales[3 * idx + 2];
+            const float q0 = rotations[4 * idx], q1 = rotations[4 * idx + 1], q2 = rotations[4 * idx + 2],
+                        q3 = rotations[4 * idx + 3];
+            cov3d_from_scale_rot(sc0, sc1, sc2, scale_modifier, q0, q1, q2, q3, cov6);
+        }
+    }
+    u32 sh_loaded = 0;           // rows of the warp's SH tile that are in shared memory
+
+    for (int v = 0; v < B; v++) {
+    const CamConst& cam = cams[v];
+    const float (*c2w)[4] = c2ws[v];
+    const float tan_fovx = s_fov[v].x, tan_fovy = s_fov[v].y;
+    const float focal_x = s_fov[v].z, focal_y = s_fov[v].w;
+    float4* rec = at_view(rec0, geom_stride, v);
     u32 my_tiles = 0;
 
     // ---- phase 1: geometry (one Gaussian per thread) ---------------------------------------------------------------
@@ -88,7 +121,6 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     ushort4 out_rect = make_ushort4(0, 0, 0, 0);
     bool emit = false;                  // survives every cull -> gets a record and a colour
     float pupil_shift = 0.f;
-    float3 p_orig = {0.f, 0.f, 0.f};
     float2 point_image = {0.f, 0.f};
     float3 conic = {0.f, 0.f, 0.f};
     float depth_z = 0.f;
@@ -96,15 +128,6 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
     const float* pm = cam.proj;
 
     if (idx < P) {
-        p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
-        // scale / rotation are fetched together with the mean (before the cull decision and the projection math):
-        // one memory round trip instead of two on the critical path of every warp; 5% of the rows are culled
-        float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-        if (!HAS_COV) {
-            sc0 = scales[3 * idx]; sc1 = scales[3 * idx + 1]; sc2 = scales[3 * idx + 2];
-            q0 = rotations[4 * idx]; q1 = rotations[4 * idx + 1]; q2 = rotations[4 * idx + 2];
-            q3 = rotations[4 * idx + 3];
-        }
         const float3 p_view = xform4x3(p_orig, vm);
 
         // Near-plane culling only (auxiliary.h:154).
@@ -130,14 +153,6 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
 
             float p_w = 1.0f / (p_hom.w + 0.0000001f);
             float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
-
-            float cov6[6];
-            if (HAS_COV) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * idx + k];
-            } else {
-                cov3d_from_scale_rot(sc0, sc1, sc2, scale_modifier, q0, q1, q2, q3, cov6);
-            }
 
             // EWA 2D covariance, forward.cu:99-164 (t.z carries the pupil shift).
             float3 t = xform4x3(p_orig, vm);
@@ -187,14 +202,16 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
                 }
             }
         }
-        radii[idx] = out_radius;
-        mean2Dx[idx] = out_mx;
-        mean2Dy[idx] = out_my;
-        depth_key[idx] = out_key;
-        rect_out[idx] = out_rect;
+        const size_t o = (size_t)v * P + idx;
+        radii[o] = out_radius;
+        mean2Dx[o] = out_mx;
+        mean2Dy[o] = out_my;
+        at_view(depth_key0, geom_stride, v)[idx] = out_key;
+        at_view(rect_out0, geom_stride, v)[idx] = out_rect;
     }
 
     // ---- phase 2: colour.  SH rows of the surviving Gaussians are staged per warp with coalesced 128-bit loads ------
+    // (a later view of a batch only fetches the rows no earlier view needed)
     float3 rgb = {0.f, 0.f, 0.f};
     u32 clamp_mask = 0;
     if (HAS_SH) {
@@ -203,11 +220,12 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         float* tile = sh_tiles + (size_t)warp * 32 * stride;
         const int warp_first = blockIdx.x * PRE_THREADS + warp * 32;
         const int rows = min(32, P - warp_first);
-        const u32 need = __ballot_sync(0xffffffffu, emit);
+        const u32 need = __ballot_sync(0xffffffffu, emit) & ~sh_loaded;
         if (need != 0 && rows > 0) {
             const float* gsh = shs + (size_t)warp_first * row_len;
             if (sh_vec4) sh_tile_load<4>(tile, stride, gsh, row_len, rows, need, lane);
             else sh_tile_load<1>(tile, stride, gsh, row_len, rows, need, lane);
+            sh_loaded |= need;
         }
         __syncwarp();
         if (emit) {
@@ -267,23 +285,29 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
         rec[3 * (size_t)idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
     }
 
-    // Block-reduce the tile-instance count; one 64-bit atomic per CTA replaces the reference's InclusiveSum +
-    // blocking 4-byte copy as the source of num_rendered.
+    // Warp-reduce the view's tile-instance count (summed per CTA after the view loop).
     u32 s = my_tiles;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    if (lane == 0) warp_sums[v][warp] = s;
+    }   // views
+
+    // One 64-bit atomic per CTA and view replaces the reference's InclusiveSum + blocking 4-byte copy as the source of
+    // num_rendered.
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < B) {
         unsigned long long tot = 0;
 #pragma unroll
-        for (int w = 0; w < PRE_THREADS / 32; w++) tot += warp_sums[w];
-        if (tot) atomicAdd(total_tiles, tot);
+        for (int w = 0; w < PRE_THREADS / 32; w++) tot += warp_sums[threadIdx.x][w];
+        if (tot) atomicAdd(at_view(total_tiles, geom_stride, threadIdx.x), tot);
     }
 }
 
+// a.viewmatrix / projmatrix / cam_pos / shift_factors: [nviews][16 | 16 | 3 | 3]; radii / mean2Dx / mean2Dy:
+// [nviews][P]; g: view 0's state, the others `geom_stride` bytes apart; fov: per-view projection constants (NULL:
+// the single view described by `a`).
 int launch_preprocess_fwd(const FwdArgs& a, GeomState& g, int* radii, float* mean2Dx, float* mean2Dy,
-                          cudaStream_t st) {
+                          cudaStream_t st, int nviews, const ViewFov* fov_in, size_t geom_stride) {
     const int gx = tiles_x(a.W), gy = tiles_y(a.H);
     const int blocks = (a.P + PRE_THREADS - 1) / PRE_THREADS;
     const bool has_sh = a.colors_precomp == nullptr;
@@ -293,6 +317,18 @@ int launch_preprocess_fwd(const FwdArgs& a, GeomState& g, int* radii, float* mea
         set_error("preprocess: %d SH coefficients per Gaussian do not fit the staging tile", a.M);
         return BAGS_E_INVALID;
     }
+    if (nviews < 1 || nviews > MAX_BATCH) {
+        set_error("preprocess: %d views in one launch (1..%d supported)", nviews, MAX_BATCH);
+        return BAGS_E_INVALID;
+    }
+    ViewFov fov;
+    if (fov_in != nullptr) {
+        fov = *fov_in;
+    } else {
+        fov.tan_fovx[0] = a.tan_fovx; fov.tan_fovy[0] = a.tan_fovy;
+        fov.focal_x[0] = a.focal_x; fov.focal_y[0] = a.focal_y;
+    }
+    if (nviews == 1) geom_stride = 0;
     if (smem > 48 * 1024) {
         BAGS_CUDA_OK(cudaFuncSetAttribute(preprocess_fwd_kernel<true, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -302,9 +338,8 @@ int launch_preprocess_fwd(const FwdArgs& a, GeomState& g, int* radii, float* mea
     const int vec4 = has_sh && ((3 * a.M) % 4 == 0) && (((size_t)a.shs & 15) == 0);
 #define BAGS_PRE_ARGS                                                                                              \
     a.P, a.D, a.M, a.means3D, a.scales, a.scale_modifier, a.rotations, a.opacities, a.shs, a.cov3D_precomp,        \
-        a.colors_precomp, a.viewmatrix, a.projmatrix, a.cam_pos, a.shift_factors, a.W, a.H, a.tan_fovx, a.tan_fovy, \
-        a.focal_x, a.focal_y, gx, gy, a.prefiltered, radii, mean2Dx, mean2Dy, g.rec, g.key_a, g.rect,           \
-        g.counters, vec4
+        a.colors_precomp, a.viewmatrix, a.projmatrix, a.cam_pos, a.shift_factors, a.W, a.H, fov, nviews, gx, gy,   \
+        a.prefiltered, radii, mean2Dx, mean2Dy, g.rec, g.key_a, g.rect, g.counters, geom_stride, vec4
     if (has_sh && has_cov)
         preprocess_fwd_kernel<true, true><<<blocks, PRE_THREADS, smem, st>>>(BAGS_PRE_ARGS);
     else if (has_sh)

@@ -17,7 +17,8 @@ reached through ``_C``, a compiled PyTorch C++ extension with the reference's fo
 (3dgs-pose/ext.cpp:15-20; source: csrc/ext.cpp); there is no CPU path.
 
 Extensions beyond the reference API (all off unless asked for): gradient sinks (``register_grad_sink`` +
-``grad_sinks()``), the asynchronous forward (``AsyncForward``).
+``grad_sinks()``), the asynchronous forward (``AsyncForward``), several cameras over the same Gaussians as one launch
+set (``GaussianBatchRasterizer``).
 """
 import contextlib
 from typing import NamedTuple
@@ -290,6 +291,168 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = torch.Tensor([])
         return rasterize_gaussians(means3D, means2D, means2D_densify, shift_factors, shs, colors_precomp, opacities,
                                    scales, rotations, cov3D_precomp, rs)
+
+
+# ---- B views of the same Gaussians as one launch set (extension) ----------------------
+class GaussianBatchRasterizer(nn.Module):
+    """Renders B cameras over the same Gaussians in ONE launch set (C ABI: bags_rasterize_forward_batch /
+    bags_rasterize_backward_batch_*).  The reference renders its five cubemap faces with five render() calls
+    (utils/cubemap_utils.py:229,265); this module takes the five `GaussianRasterizationSettings` at once:
+
+        rasterizer = GaussianBatchRasterizer([settings_0, ..., settings_{B-1}], capacity)
+        color, radii, depth, weights, mean2D = rasterizer(means3D, means2D, means2D_densify, shift_factors, opacities,
+                                                          shs=..., scales=..., rotations=...)
+
+    with `means2D` / `means2D_densify` of shape (B, P, 3) (the per-view gradient holders of render()), `shift_factors`
+    (3,) shared or (B, 3), and outputs stacked along a leading view axis: color (B,3,H,W), radii (B,P), depth / weights
+    (B,1,H,W), mean2D (B,P,2).  View v's slice is bit-identical to what `GaussianRasterizer(settings_v)` returns; the
+    gradients w.r.t. the Gaussian parameters are the sums over the views, the per-camera gradients (view matrix, camera
+    centre, projection, pupil shift) flow back to each settings' own tensors.
+
+    The views must share image size, background, scale modifier, SH degree.  `capacity` = tile instances per view the
+    binning buffers are sized for (the asynchronous protocol of `AsyncForward`: nothing waits on the host; counts land
+    in `self.counts`, pinned int64[B]; `check()` raises on an overflow once the stream has been synchronised).
+    `backward_slices` / `on_slice`: the per-Gaussian part of the backward runs in that many slices of consecutive
+    Gaussians and `on_slice(first, count)` is called after each has been enqueued -- the rows [first, first+count) of the
+    Gaussian-parameter gradients are final at that point of the stream (view-parallel trainers start the all-reduce of
+    the slice there, see bags_view_parallel.SlicedGradientReducer)."""
+
+    def __init__(self, raster_settings_list, capacity, backward_slices=1, on_slice=None):
+        super().__init__()
+        rs = list(raster_settings_list)
+        if not 1 <= len(rs) <= _C.MAX_BATCH:
+            raise ValueError(f"a batch holds 1..{_C.MAX_BATCH} views, got {len(rs)}")
+        r0 = rs[0]
+        for r in rs[1:]:
+            if (r.image_height, r.image_width, r.scale_modifier, r.sh_degree, r.prefiltered) != \
+                    (r0.image_height, r0.image_width, r0.scale_modifier, r0.sh_degree, r0.prefiltered) or \
+                    (r.bg is not r0.bg and not torch.equal(r.bg, r0.bg)):
+                raise ValueError("the views of a batch must share image size, background, scale modifier, SH degree")
+        self.raster_settings = rs
+        self.capacity = int(capacity)
+        if self.capacity < 0 or self.capacity >= (1 << 30):
+            raise ValueError("capacity must be in [0, 2^30)")
+        self.backward_slices = max(1, int(backward_slices))
+        self.on_slice = on_slice
+        self.counts = torch.full((len(rs),), -1, dtype=torch.int64).pin_memory()
+
+    def check(self):
+        m = int(self.counts.max())
+        if m > self.capacity:
+            raise RuntimeError(f"bags_b200: batched forward overflowed its binning capacity ({m} tile instances > "
+                               f"capacity {self.capacity}); re-run with capacity >= {int(m * 1.25) + (64 << 10)}")
+        return m
+
+    def forward(self, means3D, means2D, means2D_densify, shift_factors, opacities, shs=None, colors_precomp=None,
+                scales=None, rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        B = len(rs)
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        empty = torch.Tensor([])
+        shs = empty if shs is None else shs
+        colors_precomp = empty if colors_precomp is None else colors_precomp
+        scales = empty if scales is None else scales
+        rotations = empty if rotations is None else rotations
+        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        world_view = torch.stack([r.viewmatrix for r in rs])
+        full_proj = torch.stack([r.projmatrix for r in rs])
+        campos = torch.stack([r.campos.reshape(3) for r in rs])
+        if shift_factors.dim() == 1:
+            shift_factors = shift_factors.unsqueeze(0).expand(B, 3)
+        sinks = None
+        if _SINKS_ACTIVE and _GRAD_SINKS and torch.is_grad_enabled():
+            sinks = {k: b for k, b in (("means3D", _sink_of(means3D)), ("sh", _sink_of(shs)),
+                                       ("opacity", _sink_of(opacities)), ("scales", _sink_of(scales)),
+                                       ("rotations", _sink_of(rotations))) if b is not None} or None
+        return _RasterizeGaussiansBatch.apply(means3D, means2D, means2D_densify, shs, colors_precomp, opacities, scales,
+                                              rotations, cov3D_precomp, world_view, campos, full_proj, shift_factors,
+                                              self, sinks)
+
+
+class _RasterizeGaussiansBatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, means2D_densify, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, world_view, camera_center, full_proj, shift_factors, module, sinks=None):
+        rs = module.raster_settings
+        r0 = rs[0]
+        tanx = [float(r.tanfovx) for r in rs]
+        tany = [float(r.tanfovy) for r in rs]
+        out = _C.rasterize_gaussians_batch(r0.bg, means3D, shift_factors.contiguous(), colors_precomp, opacities, scales,
+                                           rotations, r0.scale_modifier, cov3Ds_precomp, world_view, full_proj, tanx,
+                                           tany, r0.image_height, r0.image_width, sh, r0.sh_degree, camera_center,
+                                           r0.prefiltered, module.capacity, module.counts)
+        color, depth, weights, radii, geomBuffer, binningBuffer, imgBuffer, means2Dx, means2Dy = out
+        mean2D = torch.cat((means2Dx, means2Dy), dim=-1)
+        ctx.set_materialize_grads(False)
+        ctx.module = module
+        ctx.tan = (tanx, tany)
+        ctx.grad_sinks = sinks
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+                              binningBuffer, imgBuffer, world_view, camera_center, full_proj)
+        ctx.mark_non_differentiable(radii, mean2D)
+        return color, radii, depth, weights, mean2D
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _, grad_out_depth, grad_out_weight, grad_mean2D):
+        module = ctx.module
+        r0 = module.raster_settings[0]
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer,
+         world_view, camera_center, full_proj) = ctx.saved_tensors
+        B, P = radii.shape
+        dev = means3D.device
+        if grad_out_color is None:
+            if grad_out_depth is None and grad_out_weight is None:
+                return (None,) * 15
+            grad_out_color = torch.zeros((B, 3, r0.image_height, r0.image_width), dtype=torch.float32, device=dev)
+        scratch = _C.rasterize_gaussians_backward_batch_blend(r0.bg, P, module.capacity, grad_out_color, grad_out_depth,
+                                                              grad_out_weight, geomBuffer, binningBuffer, imgBuffer)
+        sk = ctx.grad_sinks or {}
+        M = sh.shape[1] if sh.numel() else 0
+        f32 = dict(dtype=torch.float32, device=dev)
+        acc = 0
+
+        def out(name, bit, shape):
+            nonlocal acc
+            b = sk.get(name)
+            if b is None:
+                return torch.empty(shape, **f32), False
+            acc |= bit
+            return b, True
+        g_means3D, s_means = out("means3D", _C.ACC_MEANS3D, (P, 3))
+        g_sh, s_sh = out("sh", _C.ACC_SH, (P, M, 3))
+        g_op, s_op = out("opacity", _C.ACC_OPACITY, (P, 1))
+        g_sc, s_sc = out("scales", _C.ACC_SCALE, (P, 3))
+        g_rot, s_rot = out("rotations", _C.ACC_ROT, (P, 4))
+        g_m2d = torch.empty((B, P, 3), **f32)
+        g_m2d_dens = torch.empty((B, P, 3), **f32)
+        pose = torch.empty((38 * B,), **f32)
+        g_col = torch.empty((P, 3), **f32) if colors_precomp.numel() else None
+        g_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp.numel() else None
+        n = module.backward_slices if P > 0 else 1
+        bounds = [(P * k) // n for k in range(n + 1)]
+        for k in range(n):
+            first, count = bounds[k], bounds[k + 1] - bounds[k]
+            if count == 0 and k < n - 1:
+                continue
+            _C.rasterize_gaussians_backward_batch_gaussians(
+                means3D, radii, scales, rotations, r0.scale_modifier, cov3Ds_precomp, world_view, full_proj,
+                ctx.tan[0], ctx.tan[1], r0.image_height, r0.image_width, sh, r0.sh_degree, camera_center, geomBuffer,
+                scratch, g_m2d, g_m2d_dens, g_op, g_means3D, g_sh, g_sc, g_rot, pose, g_col, g_cov, None, acc,
+                first, count)
+            if module.on_slice is not None:
+                module.on_slice(first, count)
+        g_proj = pose[:16 * B].view(B, 4, 4)
+        g_view = pose[16 * B:32 * B].view(B, 4, 4)
+        g_campos = pose[32 * B:35 * B].view(B, 3)
+        g_shift = pose[35 * B:38 * B].view(B, 3)
+        return (None if s_means else g_means3D, g_m2d, g_m2d_dens, None if s_sh else (g_sh if M else None), g_col,
+                None if s_op else g_op, None if s_sc else (g_sc if scales.numel() else None),
+                None if s_rot else (g_rot if rotations.numel() else None), g_cov, g_view, g_campos, g_proj, g_shift,
+                None, None)
 
 
 def compute_relocation(opacity_old, scale_old, N, binoms, n_max):

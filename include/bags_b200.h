@@ -21,6 +21,8 @@
  *   bags_densify_gather           <- GaussianModel.densify_and_prune's torch.cat / masked-index surgery over the parameters
  *                                    and Adam moments, scene/gaussian_model.py:315-447
  *   bags_adam_step                <- torch.optim.Adam.step() as scene/gaussian_model.py:197-206 / train.py:420 use it
+ *   bags_rasterize_forward_batch / bags_rasterize_backward_batch_* <- B calls of the two functions above for B cameras
+ *                                    over the same Gaussians (the per-face render() loop of utils/cubemap_utils.py:229,265)
  *   bags_rasterize_forward_async  <- the same forward without the blocking read-back of num_rendered
  *                                    (rasterizer_impl.cu:291): caller-provided binning capacity, count kept on the device
  *   bags_unpack_state             (test-only) exposes the private binning/image state so parity tests can compare
@@ -247,6 +249,119 @@ int bags_rasterize_backward_accum(
     float* dL_dshift,
     unsigned accumulate_mask,
     int debug,
+    void* stream);
+
+/* ---- B views of the same Gaussians as ONE launch set (extension) -------------------------
+ * The reference renders several cameras over the same Gaussians per iteration -- the five cubemap faces of
+ * utils/cubemap_utils.py:229,265 each go through gaussian_renderer.render() -> one full rasterizer forward, and each
+ * view's backward re-reads every parameter and re-adds every gradient.  Here the B views are one batch:
+ *   - every kernel of the pipeline is launched once for all views (the view is a grid dimension), so the latency-bound
+ *     stages (depth sort of 1 M keys, emit, ranges) fill the GPU and the blend kernels' tails overlap;
+ *   - the forward preprocess reads mean / scale / rotation / SH once per Gaussian and evaluates the 3D covariance once;
+ *   - the backward preprocess reads the SH row once, sums the Gaussian-parameter gradients of the B views on chip and
+ *     writes (or, with accumulate_mask, adds) them once;
+ *   - nothing waits on the host (the asynchronous protocol of bags_rasterize_forward_async: one `capacity` per view).
+ * Per view the results are those of the single-view entry points bit for bit (images, radii, every private state
+ * array); summed gradients equal buffer + g_0 + g_1 + ... accumulated in view order.
+ *
+ * Layout: per-view inputs are stacked -- viewmatrix / projmatrix [B][16], cam_pos / shift_factors [B][3]; tan_fovx /
+ * tan_fovy are HOST arrays [B].  Per-view outputs are stacked -- out_color [B][3][H][W], out_depth / out_alpha
+ * [B][H][W], radii / mean2Dx / mean2Dy [B][P], num_rendered_out [B].  The three state buffers hold B consecutive
+ * single-view states: geom_alloc is asked for B * bags_geom_bytes(P) bytes (binning: B * bags_binning_bytes(P, capacity,
+ * ..), image: B * bags_image_bytes(..)) and must return 256-byte aligned memory; view v's state starts v * bytes in and
+ * is a valid single-view state (bags_unpack_state / bags_rasterize_backward accept it).  1 <= B <= BAGS_MAX_BATCH, all
+ * views share width, height, background, scale_modifier and the SH degree.  Returns 0 on success. */
+#define BAGS_MAX_BATCH 8
+int bags_rasterize_forward_batch(
+    int B,
+    bags_alloc_fn geom_alloc, void* geom_user,
+    bags_alloc_fn binning_alloc, void* binning_user,
+    bags_alloc_fn image_alloc, void* image_user,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    const float* shift_factors,
+    const float* tan_fovx, const float* tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_depth,
+    float* out_alpha,
+    int* radii,
+    float* mean2Dx,
+    float* mean2Dy,
+    int capacity,
+    unsigned long long* num_rendered_out,
+    void* stream);
+
+/* Backward of a batch, in two steps so that a multi-GPU caller can overlap the gradient exchange with the computation:
+ *   1. bags_rasterize_backward_batch_blend: zeroes `scratch` (bags_backward_batch_scratch_bytes(B, P) bytes) and runs the
+ *      blend backward of all B views (one grid) into it.  dL_dpix [B][3][H][W]; dL_dpix_depth / dL_dalpha [B][H][W] or NULL.
+ *   2. bags_rasterize_backward_batch_gaussians: the per-Gaussian chain rule for Gaussians [first, first + count) of ALL
+ *      views.  Call it once with (0, P), or slice by slice in ascending order; when a slice has been enqueued, the rows
+ *      [first, first + count) of the summed outputs are final -- a trainer records an event and starts the all-reduce of
+ *      that slice on another stream while the next slice computes.  The call whose slice ends at P also completes the
+ *      per-view pose / intrinsic gradients.
+ * Outputs.  Per view: dL_dmean2D, dL_dmean2D_densify [B][P][3]; covariance [B][P] (may be NULL); dL_dprojmatrix,
+ * dL_dviewmatrix [B][16]; dL_dcampos, dL_dshift [B][3].  Summed over the views: dL_dmean3D [P][3], dL_dopacity [P],
+ * dL_dsh [P][M][3], dL_dscale [P][3], dL_drot [P][4], and -- may be NULL -- dL_dcolor [P][3], dL_dcov3D [P][6].
+ * accumulate_mask (BAGS_ACC_*): the selected summed outputs are added onto the caller's buffer (rows no view sees are
+ * neither read nor written) instead of written. */
+size_t bags_backward_batch_scratch_bytes(int B, int P);
+int bags_rasterize_backward_batch_blend(
+    int B, int P, int R,
+    const float* background,
+    int width, int height,
+    const char* geom_buffer,
+    const char* binning_buffer,
+    const char* image_buffer,
+    const float* dL_dpix,
+    const float* dL_dpix_depth,
+    const float* dL_dalpha,
+    char* scratch,
+    void* stream);
+int bags_rasterize_backward_batch_gaussians(
+    int B, int P, int D, int M,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    const float* tan_fovx, const float* tan_fovy,
+    const int* radii,
+    const char* geom_buffer,
+    const char* scratch,
+    float* dL_dmean2D,
+    float* dL_dmean2D_densify,
+    float* covariance,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    float* dL_dprojmatrix,
+    float* dL_dviewmatrix,
+    float* dL_dcampos,
+    float* dL_dshift,
+    unsigned accumulate_mask,
+    int first, int count,
     void* stream);
 
 /* present[i] = (view * p_i).z > 0.2  (auxiliary.h:139-164).  `present` is one byte per point. */

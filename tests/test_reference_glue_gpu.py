@@ -92,7 +92,7 @@ def load_glue(which):
     else:
         dgr = pc.load_ref()
         d = os.path.join(pc.REF_DIR, "simple_knn")
-        spec = importlib.util.spec_from_file_location("ref_simple_knn_C", os.path.join(d, "_C.so"))
+        spec = importlib.util.spec_from_file_location("ref_simple_knn._C", os.path.join(d, "_C.so"))
         knn = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(knn)
         knn_pkg = types.ModuleType("simple_knn")

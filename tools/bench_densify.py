@@ -37,6 +37,13 @@ def main():
             del m
             torch.cuda.empty_cache()
         res[name] = {"ms": [round(t, 3) for t in times], "best_ms": round(min(times[1:]), 3), "rows_after": rows}
+    # where ours spends its time (each phase closed by a synchronisation; development aid)
+    m = T.build_model(ns, P, steps=1)
+    torch.manual_seed(1)
+    phases = {}
+    bags_densify.densify_and_prune(m, 0.0002, 0.005, 4.0, 20, _timing=phases)
+    res["ours_phases_ms"] = phases
+    del m
     res["speedup"] = round(res["reference"]["best_ms"] / res["ours"]["best_ms"], 2)
     print(json.dumps(res))
 

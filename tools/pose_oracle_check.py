@@ -55,10 +55,13 @@ def one(name, scale, shift=(0.0, 0.0, 0.0)):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    argv = sys.argv[1:]
     scale = 0.004
-    if "--scale" in sys.argv:
-        scale = float(sys.argv[sys.argv.index("--scale") + 1])
+    if "--scale" in argv:
+        k = argv.index("--scale")
+        scale = float(argv[k + 1])
+        del argv[k:k + 2]
+    args = [a for a in argv if not a.startswith("--")]
     for n in args or ["C1"]:
         one(n, scale)
         if n == "C1":
