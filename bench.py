@@ -73,8 +73,11 @@ def parse(argv=None):
                          "k's preprocess/binning/forward overlaps view k-1's backward; 1 = everything on one stream")
     ap.add_argument("--no-balance", action="store_true",
                     help="N > 1: keep the round-robin view assignment instead of balancing it by tile instances")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="N > 1: one all-reduce after the step instead of the overlapped schedule")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1, batch mode: exchange the gradients slice by slice inside the batched backward "
+                         "(bags_view_parallel.SlicedGradientReducer, NCCL stream at high priority) instead of one "
+                         "all-reduce after the step")
+    ap.add_argument("--no-overlap", action="store_true", help=argparse.SUPPRESS)     # (the default; kept for old scripts)
     ap.add_argument("--torch-loss", action="store_true",
                     help="e2e leg of our arm: the torch operator sequence of utils/loss_utils.py:18-19 (what the "
                          "reference arm always runs) instead of bags_loss.l1_loss_u8")
@@ -251,7 +254,17 @@ def main():
         # NCCL writes its debug output (the image sets NCCL_DEBUG=VERSION: a version banner) to stdout, next to the
         # one JSON line; send it to stderr whatever level the caller chose
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if args.overlap:
+            # NCCL's stream gets a high priority: the slice all-reduces that overlap the batched backward must be
+            # scheduled as soon as SM slots free up, not after the compute kernel queued behind them has dispatched all
+            # its CTAs.  (Only with --overlap: with the plain step-end all-reduce a high-priority NCCL stream was seen
+            # to hang the 2-GPU run.)
+            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
+
+    def progress(what):
+        if use_dist:
+            print(f"[bench rank {rank}] {what}", file=sys.stderr, flush=True)
 
     mod = load_impl(args.impl)
     if mod is None:
@@ -316,12 +329,22 @@ def main():
     # and bags_view_parallel.balance_views deals the same 4N views out again, the same number per rank.
     assignment = "round-robin (rank r: views r, r+N, ...)"
     if use_dist and not args.no_balance:
-        counts = []
+        # cost of a view = its measured forward + backward time (CUDA events, second of two runs): the tile-instance
+        # count is a poor proxy -- the bench cameras with the fewest instances are the slowest (larger footprints)
+        costs = []
         for vw in views:
-            c = render(vw)[0]
-            counts.append(int(c.grad_fn.num_rendered))
-            del c
-        mine = torch.tensor(counts, dtype=torch.int64, device=dev)
+            for rep_ in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                c, _, d_, w_, _ = render(vw)
+                torch.autograd.backward([c, d_, w_], vw["up"])
+                e1.record()
+                torch.cuda.synchronize()
+                del c, d_, w_
+            costs.append(int(1e3 * e0.elapsed_time(e1)))        # microseconds
+        params.zero_grad()
+        clear_pose_grads()
+        mine = torch.tensor(costs, dtype=torch.int64, device=dev)
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
         cost = [0] * nviews
@@ -331,7 +354,7 @@ def main():
         table = VP.balance_views(cost, world)
         loads = [sum(cost[v] for v in q) for q in table]
         rr = [sum(cost[v] for v in range(r, nviews, world)) for r in range(world)]
-        assignment = (f"balanced by tile instances (bags_view_parallel.balance_views): max/mean work "
+        assignment = (f"balanced by measured view time (bags_view_parallel.balance_views): max/mean work "
                       f"{max(loads) / (sum(loads) / world):.3f} (round-robin: {max(rr) / (sum(rr) / world):.3f})")
         if table[rank] != my_views:
             my_views = table[rank]
@@ -413,7 +436,7 @@ def main():
             vw["gt_dev"] = [batch["gt"][0][k], batch["gt"][1][k]]
         batch["m2d"] = torch.zeros(nb, P, 3, device=dev, requires_grad=True)
         batch["m2dd"] = torch.zeros(nb, P, 3, device=dev, requires_grad=True)
-        batch["reducer"] = VP.SlicedGradientReducer(params) if (use_dist and not args.no_overlap) else None
+        batch["reducer"] = VP.SlicedGradientReducer(params) if (use_dist and args.overlap) else None
         settings = [mod.GaussianRasterizationSettings(
             image_height=H, image_width=W, tanfovx=vw["cam"].tanfovx, tanfovy=vw["cam"].tanfovy, bg=bg,
             scale_modifier=1.0, viewmatrix=vw["view"], projmatrix=vw["proj"], intrinsic=vw["intrinsic"], sh_degree=3,
@@ -485,7 +508,7 @@ def main():
 
     overlap = None
     if use_dist:
-        overlap = None if args.no_overlap else VP.GradientReducer(params)
+        overlap = VP.GradientReducer(params)
     if batch_mode and batch["reducer"] is not None:
         overlap = batch["reducer"]
 
@@ -641,6 +664,7 @@ def main():
             all_ms.append(timed_once(fn, steps, finish))
         return median(all_ms), all_ms
 
+    progress("scene, views and step built")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     # W untimed warm-up steps, and at least ~1.5 s of them (allocator growth, clocks, page-locked staging)
     t_warm, n_warm = time.time(), 0
@@ -656,7 +680,9 @@ def main():
     launches = None
     if capi is not None and not graph_mode:
         launches0 = capi.lib().bags_launch_count()
+    progress("warm-up done")
     ms, ms_all = timed(step_device, args.steps)
+    progress("device leg timed")
     if capi is not None:
         if graph_mode:
             launches = launches_per_step * args.steps          # one replay = the captured launches of one step
@@ -712,6 +738,7 @@ def main():
                               "what": "+ 8-bit ground truth from pinned host memory (prefetched one view ahead), "
                                       "torch L1 loss (utils/loss_utils.py:18-19), loss read back"}
     clocks = sampler.stop() if sampler is not None else None
+    progress("timed legs done")
 
     # per-stage CUDA-event times (events on the launching stream, recorded inside the library) in a separate short
     # pass, so that the event records do not sit in the timed region above
@@ -729,10 +756,31 @@ def main():
         stage_ms, stage_calls = capi.profile_read()
         capi.lib().bags_profile_enable(0)
 
-    if rank != 0:
+    def leave(code=0):
+        """End of a multi-rank run: release the captured graphs (graph-captured collectives keep NCCL work alive inside
+        them; destroy_process_group() was seen to hang behind that), meet at a barrier, tear the group down -- with a
+        timer that ends the process if the teardown does not return."""
+        nonlocal cap_dev, cap_e2e
         if use_dist:
+            import gc
+            import threading
+            torch.cuda.synchronize()
+            cap_dev = cap_e2e = None
+            gc.collect()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            t = threading.Timer(15.0, lambda: os._exit(code))
+            t.daemon = True
+            t.start()
             dist.destroy_process_group()
-        return 0
+            t.cancel()
+        return code
+
+
+    if rank != 0:
+        return leave(0)
 
     value = nviews * args.steps / (ms / 1e3)
     line = {
@@ -832,9 +880,7 @@ def main():
         except Exception as ex:  # the baseline is a report, not the product
             line["cpu_baseline"] = {"error": repr(ex)}
     emit(line)
-    if use_dist:
-        dist.destroy_process_group()
-    return 0
+    return leave(0)
 
 
 if __name__ == "__main__":

@@ -231,9 +231,9 @@ class SlicedGradientReducer(GradientReducer):
     (`async_op=True`: NCCL's stream waits for the slice's kernel, the compute stream goes on with the next slice) and
     only the last slice's exchange is exposed -- instead of one 236 B/Gaussian all-reduce after the whole step.
 
-    The flat buffer is field-major (means | SH | opacity | scales | rotations): the SH rows of a slice (48 of the 59
-    floats) are one contiguous range and go per slice; the two small remaining regions (means; opacity + scales +
-    rotations) go once, after the last slice.  `finish()` makes the current stream wait for everything."""
+    The flat buffer is field-major (means | SH | opacity | scales | rotations), so a slice of Gaussians is five
+    contiguous ranges: they go as ONE coalesced all-reduce (one NCCL group launch) per slice.  `finish()` makes the
+    current stream wait for everything."""
 
     def __init__(self, params: "FlatGaussianParams", group=None):
         super().__init__(params, group)
@@ -241,21 +241,35 @@ class SlicedGradientReducer(GradientReducer):
         self._active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
     def describe(self):
-        return ("all_reduce(SUM) of each slice's SH-gradient rows as the batched backward finishes the slice "
-                "(overlapped with the next slice), the 11 small floats per Gaussian after the last slice")
+        return ("one coalesced all_reduce(SUM) of each slice's gradient rows (5 ranges, 59 floats per Gaussian) as the "
+                "batched backward finishes the slice, overlapped with the next slice")
 
-    def on_slice(self, first: int, count: int):
-        if not self._active:
-            return
+    def slice_ranges(self, first: int, count: int):
+        """The five contiguous pieces of the flat gradient buffer that hold Gaussians [first, first + count)."""
         P = self.params.P
         g = self.params.flat_grad
-        if count > 0:
-            sh0 = 3 * P
-            self._works.append(dist.all_reduce(g[sh0 + 48 * first:sh0 + 48 * (first + count)], op=dist.ReduceOp.SUM,
-                                               group=self.group, async_op=True))
-        if first + count == P:
-            self._works.append(dist.all_reduce(g[:3 * P], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-            self._works.append(dist.all_reduce(g[51 * P:], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        out, off = [], 0
+        for _, shape in FIELDS:
+            w = 1
+            for s in shape:
+                w *= s
+            out.append(g[off + w * first:off + w * (first + count)])
+            off += w * P
+        return out
+
+    def on_slice(self, first: int, count: int):
+        if not self._active or count <= 0:
+            return
+        pieces = self.slice_ranges(first, count)
+        cm_factory = getattr(dist.distributed_c10d, "_coalescing_manager", None)
+        if cm_factory is not None:
+            with cm_factory(self.group, async_ops=True) as cm:
+                for t in pieces:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self._works.append(cm)
+        else:
+            self._works.append(dist.all_reduce_coalesced(pieces, op=dist.ReduceOp.SUM, group=self.group,
+                                                         async_op=True))
 
     def finish(self):
         """The current stream waits for every all-reduce launched since the last finish()."""

@@ -389,7 +389,24 @@ __device__ __forceinline__ void warp_reduce_commit12(const float (&v)[12], const
         c = cnt;
         commit = true;
     }
-    if (commit) atomicAdd(dst + slot, c);
+    // `dst` is global memory: a plain RED instead of the generic-address atomic (which carries a shared / local window
+    // check and two CAS loops along)
+    if (commit) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + slot), "f"(c) : "memory");
+}
+
+// exp() of the backward.  The forward needs the reference's exact expf (its alpha decides thresholds and colours bit for
+// bit); the backward only needs (1) the same contribute / skip decision as the forward and (2) alpha to gradient
+// accuracy.  ex2.approx(x log2 e) is within 4e-7 relative on the range that matters (power >= -5.6): the decision is
+// re-taken with the exact expression only when alpha lands within 1e-6 of the 1/255 threshold.
+__device__ __forceinline__ float exp_bwd(const float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(const float x) {   // x in [0.01, 1]: no denormal handling needed
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 #ifdef BAGS_STATS
@@ -547,8 +564,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                     if (((cm >> wp.cell_shift(k)) & 0x33u) == 0u || pos >= pmax[k]) continue;
                     const float dy = q0.y - (pyf0 + (float)(4 * k));
                     const float power = splat_power(dx, adx, bdx, dy, con_o.z);
-                    const float Gv = exp(power);
-                    const float alpha = min(0.99f, con_o.w * Gv);
+                    float Gv = exp_bwd(power);
+                    float alpha = min(0.99f, con_o.w * Gv);
+                    if (fabsf(alpha - 1.0f / 255.0f) < 1e-6f) {      // (rare) borderline: the forward's own expression
+                        Gv = exp(power);
+                        alpha = min(0.99f, con_o.w * Gv);
+                    }
                     const bool valid = (pos < last_contributor[k]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                     const u32 vmask = __ballot_sync(FULL, valid);
                     if (vmask == 0u) continue;
@@ -565,7 +586,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                     }
                     // T_j = T_{j+1} / (1 - alpha); one (approximate, 1-ulp) reciprocal serves both divisions of
                     // backward.cu:1051,1090 -- see DESIGN.md, tolerance notes
-                    const float rcp = __fdividef(1.0f, 1.f - alpha);
+                    const float rcp = rcp_fast(1.f - alpha);
                     T[k] = T[k] * rcp;
                     const float dchannel_dcolor = alpha * T[k];
                     const float4 col = lds128(a + 32);

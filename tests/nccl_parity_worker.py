@@ -51,6 +51,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")     # the overlapped slice all-reduces must not queue behind compute
     dist.init_process_group("nccl", device_id=dev)
     mod = pc.load_ours()
     W, H, P, V = 640, 368, 200_000, 3 * world
@@ -114,12 +115,60 @@ def main():
     reducer.reduce()
     reducer.reduce_stats(stats, shift.grad)
     torch.cuda.synchronize()
+    flat_per_view = params.flat_grad.clone()
+    shift_grad_per_view = shift.grad.clone()
+
+    # ---- ours, the rank's views as ONE launch set, gradient exchange overlapped slice by slice ----------------------------
+    # (GaussianBatchRasterizer + SlicedGradientReducer; run eagerly, then captured in a CUDA graph -- NCCL calls included)
+    sliced = VP.SlicedGradientReducer(params)
+    settings = [mod.GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cams[v].tanfovx, tanfovy=cams[v].tanfovy, bg=bg, scale_modifier=1.0,
+        viewmatrix=leaves[v][0], projmatrix=leaves[v][1], intrinsic=leaves[v][3], sh_degree=3, campos=leaves[v][2],
+        prefiltered=False, debug=False, debug_iter=0) for v in mine]
+    brast = mod.GaussianBatchRasterizer(settings, 6_000_000, backward_slices=3, on_slice=sliced.on_slice)
+    bm2d = torch.zeros(len(mine), P, 3, device=dev, requires_grad=True)
+    bm2dd = torch.zeros(len(mine), P, 3, device=dev, requires_grad=True)
+    bups = [torch.stack([ups[v][k] for v in mine]).contiguous() for k in range(3)]
+    bshift = shift0.to(dev).requires_grad_(True)
+
+    def batch_body():
+        params.zero_grad()
+        with params.accumulating():
+            color, radii, depth, weights, _ = brast(means3D=params["means3D"], means2D=bm2d, means2D_densify=bm2dd,
+                                                    shift_factors=bshift, opacities=params["opacities"],
+                                                    shs=params["shs"], scales=params["scales"],
+                                                    rotations=params["rotations"])
+            torch.autograd.backward([color, depth, weights], bups)
+        sliced.finish()
+
+    def batch_clear():
+        clear()
+        bm2d.grad = bm2dd.grad = bshift.grad = None
+
+    # every rank takes the same path here: the collectives are part of the body, so the eager warm-up runs of the capture
+    # and the replay must happen on all ranks alike
+    batch_clear()
+    batch_body()                                  # eager
+    torch.cuda.synchronize()
+    brast.check()
+    flat_batch_eager = params.flat_grad.clone()
+    batch_clear()
+    bstep = VP.CapturedStep(batch_body, dev, mod, None, forwards_per_step=1, reset=batch_clear, check=brast.check)
+    bstep.replay()
+    torch.cuda.synchronize()
+    bstep.check()
+    batch_graph_ok = pc.rel_l2(params.flat_grad.cpu(), flat_batch_eager.cpu()) <= 1e-5
+    flat_batch = params.flat_grad.clone()
+    batch_pose_local = {v: torch.cat([leaves[v][0].grad.flatten(), leaves[v][1].grad.flatten(),
+                                      leaves[v][2].grad]).cpu() for v in mine}
+    batch_m2d_ok = batch_graph_ok and all(pc.rel_l2(bm2d.grad[k].cpu(), m2d_grads[v].cpu()) <= 1e-5
+                                          for k, v in enumerate(mine))
 
     # ---- gather the per-camera pose gradients for the check on rank 0 --------------------------------------------------
     pose_local = {v: torch.cat([leaves[v][0].grad.flatten(), leaves[v][1].grad.flatten(), leaves[v][2].grad]).cpu()
                   for v in mine}
     gathered = [None] * world
-    dist.all_gather_object(gathered, (mine, pose_local, schedule))
+    dist.all_gather_object(gathered, (mine, pose_local, schedule, batch_pose_local, batch_m2d_ok))
 
     ok, report = True, {}
     if rank == 0:
@@ -142,8 +191,11 @@ def main():
             n = P
             for s_ in shape:
                 n *= s_
-            e = pc.rel_l2(params.flat_grad[off:off + n].cpu(), rparams.flat_grad[off:off + n].cpu())
+            e = pc.rel_l2(flat_per_view[off:off + n].cpu(), rparams.flat_grad[off:off + n].cpu())
             report["grad_" + name] = e
+            ok &= e <= 1e-4
+            e = pc.rel_l2(flat_batch[off:off + n].cpu(), rparams.flat_grad[off:off + n].cpu())
+            report["batch_grad_" + name] = e
             ok &= e <= 1e-4
             off += n
         for k in ("accum", "accum_abs", "denom"):
@@ -152,17 +204,21 @@ def main():
             ok &= e <= 1e-4
         report["max_radii2D_mismatch"] = int((stats.max_radii2D != rstats.max_radii2D).sum())
         ok &= report["max_radii2D_mismatch"] == 0
-        report["shift_grad"] = pc.rel_l2(shift.grad.cpu(), rshift.grad.cpu())
+        report["shift_grad"] = pc.rel_l2(shift_grad_per_view.cpu(), rshift.grad.cpu())
         ok &= report["shift_grad"] <= 1e-4
         worst = 0.0
         owners = {}
-        for r_, (views_r, pose_r, sched) in enumerate(gathered):
+        worst_b = 0.0
+        for r_, (views_r, pose_r, sched, bpose_r, bm2d_ok) in enumerate(gathered):
+            ok &= bool(bm2d_ok)
             for v in views_r:
                 owners[v] = (r_, sched)
                 # view matrix block [0:16] is the reference's racy term (Q13): compare proj + campos
                 worst = max(worst, pc.rel_l2(pose_r[v][16:], rpose[v][16:]))
+                worst_b = max(worst_b, pc.rel_l2(bpose_r[v][16:], rpose[v][16:]))
         report["pose_proj_campos_worst"] = worst
-        ok &= worst <= 1e-4 and sorted(owners) == list(range(V))
+        report["batch_pose_proj_campos_worst"] = worst_b
+        ok &= worst <= 1e-4 and worst_b <= 1e-4 and sorted(owners) == list(range(V))
         report["assignment"] = table
         report["schedules"] = [g[2] for g in gathered]
         report["world"] = world
@@ -172,8 +228,12 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     params.disable_direct_accumulation()
-    dist.destroy_process_group()
-    return 0 if int(flag) == 1 else 1
+    rc = 0 if int(flag) == 1 else 1
+    torch.cuda.synchronize()
+    del bstep                                  # the captured graph holds NCCL work: release it before the group goes
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(rc)                               # (destroy_process_group after graph-captured collectives was seen to hang)
 
 
 if __name__ == "__main__":

@@ -102,6 +102,26 @@ def _worker(rank, world, port, out_dir):
     VP.run_views(fp, views, _oracle_view_loss, rank=rank, world=world, assignment=table)
     torch.save({"grad": fp.flat_grad.clone(), "table": table, "costs": costs},
                os.path.join(out_dir, f"balanced_{rank}.pt"))
+    # third: the sliced exchange (SlicedGradientReducer) -- the buffer is final slice by slice, as the batched backward
+    # leaves it; every element must be summed exactly once whatever the slice boundaries are
+    g = torch.Generator().manual_seed(7 + rank)
+    local = torch.randn(fp.flat_grad.shape, generator=g)
+    results = {}
+    for bounds in ([0, P], [0, 100, 101, 101, 299, P], [0, 1, P - 1, P]):
+        fp.flat_grad.copy_(local)
+        red = VP.SlicedGradientReducer(fp)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            red.on_slice(a, b - a)
+        red.finish()
+        results[tuple(bounds)] = fp.flat_grad.clone()
+    stats = VP.DensificationStats(P, "cpu")
+    stats.accum.fill_(1.0 + rank)
+    stats.denom.fill_(1.0)
+    stats.max_radii2D.fill_(float(10 + rank))
+    sg = torch.full((3,), float(rank + 1))
+    VP.GradientReducer(fp).reduce_stats(stats, sg)
+    torch.save({"local": local, "sliced": results, "accum": stats.accum.clone(), "denom": stats.denom.clone(),
+                "max_radii2D": stats.max_radii2D.clone(), "shift_grad": sg}, os.path.join(out_dir, f"sliced_{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -130,3 +150,14 @@ def test_two_ranks_equal_sum_of_single_view_gradients(tmp_path):
     assert torch.equal(b0["grad"], b1["grad"])
     rel = float((b0["grad"] - fp.flat_grad).norm() / fp.flat_grad.norm())
     assert rel < 1e-5, rel
+    # sliced exchange: every slicing gives the plain sum of the two ranks' buffers, bit for bit on both ranks
+    s0 = torch.load(os.path.join(tmp_path, "sliced_0.pt"))
+    s1 = torch.load(os.path.join(tmp_path, "sliced_1.pt"))
+    want = s0["local"] + s1["local"]
+    assert len(s0["sliced"]) == 3
+    for k, v in s0["sliced"].items():
+        assert torch.equal(v, want), k
+        assert torch.equal(s1["sliced"][k], want), k
+    # small collectives: SUM over [accum | accum_abs | denom | shift grad], MAX over max_radii2D
+    assert float(s0["accum"][0]) == 3.0 and float(s0["denom"][0]) == 2.0 and float(s0["max_radii2D"][0]) == 11.0
+    assert torch.equal(s0["shift_grad"], torch.full((3,), 3.0)) and torch.equal(s1["shift_grad"], s0["shift_grad"])
