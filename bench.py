@@ -333,7 +333,8 @@ def main():
         # count is a poor proxy -- the bench cameras with the fewest instances are the slowest (larger footprints)
         costs = []
         for vw in views:
-            for rep_ in range(2):
+            best = None
+            for rep_ in range(5):                               # first run untimed, then the fastest of four
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 c, _, d_, w_, _ = render(vw)
@@ -341,7 +342,10 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 del c, d_, w_
-            costs.append(int(1e3 * e0.elapsed_time(e1)))        # microseconds
+                if rep_ > 0:
+                    t = e0.elapsed_time(e1)
+                    best = t if best is None else min(best, t)
+            costs.append(int(1e3 * best))                       # microseconds
         params.zero_grad()
         clear_pose_grads()
         mine = torch.tensor(costs, dtype=torch.int64, device=dev)
