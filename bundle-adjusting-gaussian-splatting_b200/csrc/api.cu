@@ -117,7 +117,7 @@ BinningState BinningState::from(char* p, int R, int npass) {
 size_t ImageState::bytes(int width, int height) {
     size_t N = (size_t)width * height;
     size_t T = (size_t)tiles_x(width) * tiles_y(height);
-    return 2 * align_up(N * 4) + align_up(T * sizeof(uint2)) + 256;
+    return 2 * align_up(N * 4) + align_up(T * sizeof(uint2)) + 3 * align_up(T * sizeof(u32)) + 256;
 }
 
 ImageState ImageState::from(char* p, int width, int height) {
@@ -128,6 +128,9 @@ ImageState ImageState::from(char* p, int width, int height) {
     carve(p, s.final_T, N);
     carve(p, s.n_contrib, N);
     carve(p, s.ranges, T);
+    carve(p, s.fwd_order, T);
+    carve(p, s.bwd_cost, T);
+    carve(p, s.bwd_order, T);
     return s;
 }
 

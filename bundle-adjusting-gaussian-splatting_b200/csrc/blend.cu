@@ -176,12 +176,15 @@ __global__ void __launch_bounds__(256 / PPT)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float4* __restrict__ rec, float* __restrict__ final_T, u32* __restrict__ n_contrib,
                  const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ out_depth,
-                 float* __restrict__ out_alpha, const bool cull, const ViewStride vs) {
+                 float* __restrict__ out_alpha, const bool cull, const ViewStride vs,
+                 const u32* __restrict__ order, u32* __restrict__ bwd_cost, const u32 grid_x) {
     constexpr int NT = 256 / PPT;
     constexpr int NBUF = ASYNC ? 2 : 1;
     if (blockIdx.z != 0) {   // batched launch: blockIdx.z = view, the images of the views are stacked
         const unsigned v = blockIdx.z;
         const size_t pl = (size_t)H * W * v;
+        order = at_view(order, vs.img, v);
+        bwd_cost = at_view(bwd_cost, vs.img, v);
         ranges = at_view(ranges, vs.img, v);
         final_T = at_view(final_T, vs.img, v);
         n_contrib = at_view(n_contrib, vs.img, v);
@@ -198,9 +201,12 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
 
     const int tid = threadIdx.x, lane = tid & 31;
     const WarpPixels<PPT> wp(tid >> 5);
-    const u32 px = blockIdx.x * TILE_X + wp.lx(lane);
+    // CTA i works on the i-th longest tile list (see tile_order_kernel)
+    const u32 tile_id = order[blockIdx.x];
+    const u32 tile_y = tile_id / grid_x, tile_x = tile_id - tile_y * grid_x;
+    const u32 px = tile_x * TILE_X + wp.lx(lane);
     const float pxf = (float)px;
-    const float tx0 = (float)(blockIdx.x * TILE_X), ty0 = (float)(blockIdx.y * TILE_Y);
+    const float tx0 = (float)(tile_x * TILE_X), ty0 = (float)(tile_y * TILE_Y);
 
     u32 py[PPT];
     float pyf[PPT];
@@ -209,7 +215,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     u32 last_contributor[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        py[k] = blockIdx.y * TILE_Y + wp.ly(lane, k);
+        py[k] = tile_y * TILE_Y + wp.ly(lane, k);
         pyf[k] = (float)py[k];
         inside[k] = px < (u32)W && py[k] < (u32)H;
         done[k] = !inside[k];
@@ -218,7 +224,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
         last_contributor[k] = 0;
     }
 
-    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+    const uint2 range = ranges[tile_id];
     const int rounds = ((range.y - range.x + BATCH - 1) / BATCH);
     int toDo = range.y - range.x;
 
@@ -305,6 +311,22 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     }
 
     if (ASYNC) cp_async_wait<0>();   // nothing may be in flight into shared memory when the CTA retires
+    // the tile's cost in the backward: the list positions it will walk = the largest n_contrib of its pixels
+    {
+        __shared__ u32 s_cmax[NT / 32];
+        u32 m = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; k++) m = max(m, inside[k] ? last_contributor[k] : 0u);
+        m = __reduce_max_sync(FULL, m);
+        __syncthreads();             // (also: everyone has left the staging buffers)
+        if (lane == 0) s_cmax[tid >> 5] = m;
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 1; w < NT / 32; w++) m = max(m, s_cmax[w]);
+            bwd_cost[tile_id] = m;
+        }
+    }
     const size_t plane = (size_t)H * W;
     const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 #pragma unroll
@@ -324,11 +346,15 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st, int nviews,
                      const ViewStride& vs) {
-    dim3 grid(tiles_x(W), tiles_y(H), nviews > 1 ? nviews : 1);
+    const int ntiles = tiles_x(W) * tiles_y(H);
+    int rc = launch_tile_order(ntiles, img.ranges, nullptr, img.fwd_order, st, nviews, vs);
+    if (rc) return rc;
+    dim3 grid(ntiles, 1, nviews > 1 ? nviews : 1);
 #define BAGS_FWD(PPT, ASYNC)                                                                                     \
     blend_fwd_kernel<PPT, ASYNC><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, g.rec, img.final_T, \
                                                             img.n_contrib, bg, out_color, out_depth, out_alpha, \
-                                                            g_cull != 0, vs)
+                                                            g_cull != 0, vs, img.fwd_order, img.bwd_cost,       \
+                                                            (u32)tiles_x(W))
     if (g_staging) {
         if (g_fwd_ppt == 4) BAGS_FWD(4, true);
         else if (g_fwd_ppt == 2) BAGS_FWD(2, true);
@@ -420,12 +446,13 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                  const float* __restrict__ final_Ts, const u32* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
                  const float* __restrict__ dL_dalphas, float* __restrict__ gacc, const bool cull, const ViewStride vs,
-                 const size_t gacc_stride) {
+                 const size_t gacc_stride, const u32* __restrict__ order, const u32 grid_x) {
     constexpr int NT = 256 / PPT;
     constexpr int NW = NT / 32;
     if (blockIdx.z != 0) {   // batched launch: blockIdx.z = view
         const unsigned v = blockIdx.z;
         const size_t pl = (size_t)H * W * v;
+        order = at_view(order, vs.img, v);
         ranges = at_view(ranges, vs.img, v);
         final_Ts = at_view(final_Ts, vs.img, v);
         n_contrib = at_view(n_contrib, vs.img, v);
@@ -447,10 +474,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const WarpPixels<PPT> wp(warp);
-    const u32 px = blockIdx.x * TILE_X + wp.lx(lane);
+    const u32 tile_id = order[blockIdx.x];             // CTA i works on the tile with the i-th largest n_contrib
+    const u32 tile_y = tile_id / grid_x, tile_x = tile_id - tile_y * grid_x;
+    const u32 px = tile_x * TILE_X + wp.lx(lane);
     const float pxf = (float)px;
-    const float tx0 = (float)(blockIdx.x * TILE_X), ty0 = (float)(blockIdx.y * TILE_Y);
-    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+    const float tx0 = (float)(tile_x * TILE_X), ty0 = (float)(tile_y * TILE_Y);
+    const uint2 range = ranges[tile_id];
     const size_t plane = (size_t)H * W;
     const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
@@ -461,7 +490,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     __shared__ __align__(16) float4 sm_g[G_IN_SMEM ? 256 : 1];   // {dL_dR, dL_dG, dL_dB, dL_ddepth}
     __shared__ __align__(8) float2 sm_w[G_IN_SMEM ? 256 : 1];    // {dL_dweight, -T_final * (bg . dL_dcolour)}
     const u32 s_g = smem_addr(sm_g), s_w = smem_addr(sm_w);
-    const float pyf0 = (float)(blockIdx.y * TILE_Y + wp.ly(lane, 0));   // row of pixel k is pyf0 + 4k (exact)
+    const float pyf0 = (float)(tile_y * TILE_Y + wp.ly(lane, 0));   // row of pixel k is pyf0 + 4k (exact)
     float T[PPT], Dacc[PPT];
     float g0[G_IN_SMEM ? 1 : PPT], g1[G_IN_SMEM ? 1 : PPT], g2[G_IN_SMEM ? 1 : PPT], gd[G_IN_SMEM ? 1 : PPT],
         gw[G_IN_SMEM ? 1 : PPT], nTbg[G_IN_SMEM ? 1 : PPT];
@@ -469,7 +498,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     u32 warp_max = 0;
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        const u32 py = blockIdx.y * TILE_Y + wp.ly(lane, k);
+        const u32 py = tile_y * TILE_Y + wp.ly(lane, k);
         const bool inside = px < (u32)W && py < (u32)H;
         const u32 pix_id = (u32)W * py + px;
         const float T_final = inside ? final_Ts[pix_id] : 0;
@@ -571,9 +600,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                         alpha = min(0.99f, con_o.w * Gv);
                     }
                     const bool valid = (pos < last_contributor[k]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                    const u32 vmask = __ballot_sync(FULL, valid);
-                    if (vmask == 0u) continue;
-                    nvalid += __popc(vmask);
+                    nvalid += __popc(__ballot_sync(FULL, valid));
                     if (!valid) continue;
                     float G0, G1, G2, GD, GW, NTBG;
                     if (G_IN_SMEM) {
@@ -634,11 +661,15 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
 int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, const ImageState& img, const float* bg,
                      const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalpha, float* gacc,
                      cudaStream_t st, int nviews, const ViewStride& vs, size_t gacc_stride) {
-    dim3 grid(tiles_x(W), tiles_y(H), nviews > 1 ? nviews : 1);
+    const int ntiles = tiles_x(W) * tiles_y(H);
+    int rc = launch_tile_order(ntiles, nullptr, img.bwd_cost, img.bwd_order, st, nviews, vs);
+    if (rc) return rc;
+    dim3 grid(ntiles, 1, nviews > 1 ? nviews : 1);
 #define BAGS_BWD(PPT, ASYNC)                                                                                     \
     blend_bwd_kernel<PPT, ASYNC><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec,          \
                                                             img.final_T, img.n_contrib, dL_dpix, dL_dpix_depth, \
-                                                            dL_dalpha, gacc, g_cull != 0, vs, gacc_stride)
+                                                            dL_dalpha, gacc, g_cull != 0, vs, gacc_stride,      \
+                                                            img.bwd_order, (u32)tiles_x(W))
     if (g_staging) {
         if (g_bwd_ppt == 4) BAGS_BWD(4, true);
         else if (g_bwd_ppt == 2) BAGS_BWD(2, true);

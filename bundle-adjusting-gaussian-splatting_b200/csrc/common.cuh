@@ -134,6 +134,10 @@ struct ImageState {
     float* final_T;   // [N]
     u32* n_contrib;   // [N]
     uint2* ranges;    // [tiles]
+    // longest-first launch order of the blend CTAs (see tile_order_kernel): CTA i of a blend grid works on tile order[i]
+    u32* fwd_order;   // [tiles] tiles by descending list length
+    u32* bwd_cost;    // [tiles] largest n_contrib of the tile's pixels (written by the forward blend)
+    u32* bwd_order;   // [tiles] tiles by descending bwd_cost
     static size_t bytes(int width, int height);
     static ImageState from(char* p, int width, int height);
 };
@@ -216,6 +220,10 @@ int set_sort_hwmatch(int value);
 int set_pbwd_min_blocks(int value);
 int launch_ranges(int R, const unsigned long long* R_dev, int ntiles, const u32* tile_sorted, uint2* ranges,
                   cudaStream_t st, int nviews = 1, const ViewStride& vs = ViewStride());
+// order[i] = i-th tile in descending `cost` (cost = list length when `ranges` is given, else cost_in[tile]); one launch
+// for the views of a batch
+int launch_tile_order(int ntiles, const uint2* ranges, const u32* cost_in, u32* order, cudaStream_t st, int nviews = 1,
+                      const ViewStride& vs = ViewStride());
 int launch_blend_fwd(int W, int H, const GeomState& g, const BinningState& b, ImageState& img, const float* bg,
                      float* out_color, float* out_depth, float* out_alpha, cudaStream_t st, int nviews = 1,
                      const ViewStride& vs = ViewStride());
