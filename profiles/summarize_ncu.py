@@ -106,11 +106,13 @@ def full(path):
 STAGE_OF = {"preprocess_fwd_kernel": "preprocess", "emit_count_kernel": "emit", "emit_scan_kernel": "emit",
             "emit_fill_kernel": "emit", "tile_ranges_kernel": "ranges", "blend_fwd_kernel": "blend_fwd",
             "blend_bwd_kernel": "blend_bwd", "preprocess_bwd_kernel": "preprocess_bwd",
-            "pose_finalize_kernel": "preprocess_bwd"}
+            "preprocess_bwd_batch_kernel": "preprocess_bwd", "pose_finalize_kernel": "preprocess_bwd"}
 
 
-def traffic(path):
-    """Per-stage DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per view from an `ncu --set full` capture
+def traffic(path, views_per_launch=1):
+    """(`views_per_launch` > 1: a capture of the batched launch set, tools/ncu_target_batch.py -- every launch covers
+    that many views.)
+    Per-stage DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per view from an `ncu --set full` capture
     of whole views (tools/ncu_target.py); the sort kernels are attributed to the depth sort until the emit kernels of
     the view have run and to the tile sort afterwards.  Prints the JSON that bench.py reads (profiles/ncu_traffic.json)."""
     import json
@@ -125,14 +127,18 @@ def traffic(path):
         return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "us": 1e-3, "ms": 1, "ns": 1e-6,
                     "s": 1e3}.get(u, 1)
 
-    stages, views, sort_stage = OrderedDict(), 0, "depth_sort"
+    stages, views, sort_stage, order_stage = OrderedDict(), 0, "depth_sort", "blend_fwd"
     for r in rows[2:]:
         name = r[ix["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
         if name == "preprocess_fwd_kernel":
-            views += 1
+            views += int(views_per_launch)
             sort_stage = "depth_sort"
+            order_stage = "blend_fwd"
         if name in ("sort_hist_kernel", "onesweep_pass_kernel"):
             st = sort_stage
+        elif name == "tile_order_kernel":      # first launch of a view: forward order, second: backward order
+            st = order_stage
+            order_stage = "blend_bwd"
         elif name in STAGE_OF:
             st = STAGE_OF[name]
         else:
@@ -145,6 +151,7 @@ def traffic(path):
         a["launches"] += 1
     views = max(views, 1)
     out = {"_source": os.path.basename(path), "_views": views,
+           "_views_per_launch": int(views_per_launch),
            "_note": "per view: sums over the kernels of a stage divided by the number of captured views; ncu times are "
                     "serialised and cold-cache"}
     for st, a in stages.items():
@@ -154,4 +161,4 @@ def traffic(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
