@@ -88,7 +88,7 @@ def parse(argv=None):
 
 
 TUNE_KNOBS = {"BLEND_FWD_PPT": 0, "BLEND_BWD_PPT": 1, "BLEND_CULL": 2, "SORT_LOOKBACK": 3, "SORT_SMALL_TILES": 4,
-              "SORT_HWMATCH": 5, "PBWD_MIN_BLOCKS": 6, "BLEND_STAGING": 7}
+              "SORT_HWMATCH": 5, "PBWD_MIN_BLOCKS": 6, "BLEND_STAGING": 7, "BLEND_BWD_REDUCE": 8}
 
 
 def load_impl(name):
@@ -446,9 +446,12 @@ def main():
             scale_modifier=1.0, viewmatrix=vw["view"], projmatrix=vw["proj"], intrinsic=vw["intrinsic"], sh_degree=3,
             campos=vw["campos"], prefiltered=False, debug=False, debug_iter=0) for vw in views]
         red = batch["reducer"]
+        # the rank's views are ONE batch per step: its summed gradients replace the flat gradient buffer (sink_overwrite),
+        # which therefore needs no zero fill at the start of the step
         batch["rast"] = mod.GaussianBatchRasterizer(settings, capacity,
                                                     backward_slices=args.bwd_slices if red is not None else 1,
-                                                    on_slice=red.on_slice if red is not None else None)
+                                                    on_slice=red.on_slice if red is not None else None,
+                                                    sink_overwrite=grad_sinks)
 
     def render_batch():
         return batch["rast"](means3D=params["means3D"], means2D=batch["m2d"], means2D_densify=batch["m2dd"],
@@ -461,7 +464,8 @@ def main():
             batch["m2d"].grad = batch["m2dd"].grad = None
 
     def body_device_batch():
-        params.zero_grad()
+        if not grad_sinks:
+            params.zero_grad()
         with params.accumulating():
             color, radii, depth, weights, _ = render_batch()
             torch.autograd.backward([color, depth, weights], batch["up"])
@@ -469,7 +473,8 @@ def main():
             batch["reducer"].finish()
 
     def body_e2e_batch(buf):
-        params.zero_grad()
+        if not grad_sinks:
+            params.zero_grad()
         with params.accumulating():
             color, radii, depth, weights, _ = render_batch()
             # sum over the views of each view's mean L1 = (number of views) x the mean over the stacked images
@@ -825,7 +830,9 @@ def main():
               f"(binning capacity {capacity} tile instances), one launch per step") if graph_mode
         else "eager launches, blocking forward",
         "streams": 1 if batch_mode else pipe.depth, "view_assignment": assignment,
-        "grad_accumulation": "kernel adds into the flat gradient buffer (register_grad_sink)" if grad_sinks
+        "grad_accumulation": ("the batched backward writes the views' summed gradients into the flat gradient buffer "
+                              "(register_grad_sink, sink_overwrite)") if (grad_sinks and batch_mode)
+        else "kernel adds into the flat gradient buffer (register_grad_sink)" if grad_sinks
         else "autograd (fresh gradient tensors + add)",
         "allreduce": (overlap.describe() if overlap is not None else "one all_reduce after the step") if use_dist
         else None}

@@ -40,6 +40,7 @@ static int g_fwd_ppt = 2;
 static int g_bwd_ppt = 2;
 static int g_cull = 1;   // 0: every splat of the tile list is evaluated for every patch (debugging / tests)
 static int g_staging = 0;   // 1: cp.async double-buffered batch staging (see stage_issue); 0: ldg -> sts, one buffer
+static int g_bwd_reduce = 1;   // 1 (default): per-splat warp reduction of the backward through shared memory; 0: shuffle butterfly
 
 // Tile decomposition.  Cell grid: 4 columns of 4 pixels x 8 rows of 2 pixels, bit = row * 4 + column.  Patch (x, y),
 // x in 0..1, y in 0..3, is the 8x4 pixel block at (8x, 4y) = cells {2x, 2x+1} x {2y, 2y+1} = bits 0x33 << (8y + 2x).
@@ -435,11 +436,41 @@ __device__ __forceinline__ float rcp_fast(const float x) {   // x in [0.01, 1]: 
     return y;
 }
 
+// The same reduction through shared memory (BAGS_TUNE_BLEND_BWD_REDUCE = 1): every lane stores its 12 partial sums as
+// one 48-byte row (3 STS.128; rows of lanes 16..31 shifted by one row so that the two halves fall on different banks),
+// lane L < 24 then adds slot L % 12 over the 16 rows of half L / 12 (16 conflict-free LDS + a 4-level add tree), one
+// shuffle joins the halves, and lanes 0..12 commit as above.  About 45 instructions per (warp, splat) instead of 68.
+constexpr int RED_ROWS = 33;                      // 32 lanes + the padding row between the halves
+constexpr int RED_WARP_BYTES = RED_ROWS * 48;
+__device__ __forceinline__ void warp_reduce_commit12_smem(const float (&v)[12], const float cnt, const int lane,
+                                                          float* dst, const u32 s_red /* this warp's buffer */) {
+    __syncwarp();                                 // the previous splat's rows have been read by everyone
+    const u32 row = s_red + (u32)(lane + (lane >> 4)) * 48u;
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + 16u), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + 32u), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]) : "memory");
+    __syncwarp();
+    const int half = lane >= 12 ? 1 : 0;          // lanes 24..31 read along harmlessly (slots 0..7 of half 1 again)
+    const int slot = lane - 12 * half - (lane >= 24 ? 12 : 0);
+    const u32 col = s_red + (u32)(half * 17) * 48u + (u32)slot * 4u;
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)      // ("memory": the loads must stay behind the warp barrier above)
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[i]) : "r"(col + (u32)i * 48u) : "memory");
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; i++) x[i] += x[i + w];
+    float c = x[0] + __shfl_down_sync(FULL, x[0], 12);
+    if (lane == 12) c = cnt;                      // GA_COV = 12: the contributing-pixel count rides in the same RED
+    if (lane <= 12) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + lane), "f"(c) : "memory");
+}
+
 #ifdef BAGS_STATS
 __device__ unsigned long long g_stats[64];
 #endif
 
-template <int PPT, bool ASYNC>
+template <int PPT, bool ASYNC, bool REDSM>
 __global__ void __launch_bounds__(256 / PPT)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point_list, int W, int H,
                  const float* __restrict__ bg_color, const float4* __restrict__ rec,
@@ -468,6 +499,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
     __shared__ u32 sm_cell[NBUF][BATCH];
     __shared__ u32 sm_id[NBUF][BATCH];
     __shared__ u32 s_wmax[NW];
+    __shared__ __align__(16) unsigned char sm_red[REDSM ? NW * RED_WARP_BYTES : 16];
     const u32 s_rec0 = smem_addr(sm_rec);
     const u32 s_cell0 = smem_addr(sm_cell);
     const u32 s_id0 = smem_addr(sm_id);
@@ -651,7 +683,10 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ point
                 if (lane == 0) atomicAdd(&g_stats[min(nvalid, 63u)], 1ull);
 #endif
                 if (nvalid == 0u) continue;
-                warp_reduce_commit12(v, (float)nvalid, lane, gacc + (size_t)lds32(s_id + j * 4) * GACC_STRIDE);
+                float* rec_out = gacc + (size_t)lds32(s_id + j * 4) * GACC_STRIDE;
+                if (REDSM) warp_reduce_commit12_smem(v, (float)nvalid, lane, rec_out,
+                                                     smem_addr(sm_red) + (u32)warp * (u32)RED_WARP_BYTES);
+                else warp_reduce_commit12(v, (float)nvalid, lane, rec_out);
             }
         }
     }
@@ -666,7 +701,9 @@ int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, co
     if (rc) return rc;
     dim3 grid(ntiles, 1, nviews > 1 ? nviews : 1);
 #define BAGS_BWD(PPT, ASYNC)                                                                                     \
-    blend_bwd_kernel<PPT, ASYNC><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec,          \
+    if (g_bwd_reduce) BAGS_BWD_R(PPT, ASYNC, true); else BAGS_BWD_R(PPT, ASYNC, false)
+#define BAGS_BWD_R(PPT, ASYNC, REDSM)                                                                            \
+    blend_bwd_kernel<PPT, ASYNC, REDSM><<<grid, 256 / PPT, 0, st>>>(img.ranges, b.point_list, W, H, bg, g.rec,   \
                                                             img.final_T, img.n_contrib, dL_dpix, dL_dpix_depth, \
                                                             dL_dalpha, gacc, g_cull != 0, vs, gacc_stride,      \
                                                             img.bwd_order, (u32)tiles_x(W))
@@ -680,6 +717,7 @@ int launch_blend_bwd(int W, int H, const GeomState& g, const BinningState& b, co
         else BAGS_BWD(1, false);
     }
 #undef BAGS_BWD
+#undef BAGS_BWD_R
     BAGS_LAUNCH_OK("blend_bwd_kernel");
     return 0;
 }
@@ -702,6 +740,11 @@ extern "C" int bags_set_tuning(int knob, int value) {
     if (knob == BAGS_TUNE_BLEND_CULL) {
         const int prev = bags::g_cull;
         if (value == 0 || value == 1) bags::g_cull = value;
+        return prev;
+    }
+    if (knob == BAGS_TUNE_BLEND_BWD_REDUCE) {
+        const int prev = bags::g_bwd_reduce;
+        if (value == 0 || value == 1) bags::g_bwd_reduce = value;
         return prev;
     }
     if (knob == BAGS_TUNE_BLEND_STAGING) {

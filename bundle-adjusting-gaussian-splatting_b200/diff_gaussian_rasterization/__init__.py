@@ -315,9 +315,12 @@ class GaussianBatchRasterizer(nn.Module):
     `backward_slices` / `on_slice`: the per-Gaussian part of the backward runs in that many slices of consecutive
     Gaussians and `on_slice(first, count)` is called after each has been enqueued -- the rows [first, first+count) of the
     Gaussian-parameter gradients are final at that point of the stream (view-parallel trainers start the all-reduce of
-    the slice there, see bags_view_parallel.SlicedGradientReducer)."""
+    the slice there, see bags_view_parallel.SlicedGradientReducer).
+    `sink_overwrite`: with active gradient sinks, this batch's summed gradients REPLACE the contents of the sink buffers
+    (every row is written, zeros for the Gaussians no view sees) instead of being added onto them -- for the first, or
+    only, batch of an accumulation step: the buffer needs no zeroing beforehand and is not read back."""
 
-    def __init__(self, raster_settings_list, capacity, backward_slices=1, on_slice=None):
+    def __init__(self, raster_settings_list, capacity, backward_slices=1, on_slice=None, sink_overwrite=False):
         super().__init__()
         rs = list(raster_settings_list)
         if not 1 <= len(rs) <= _C.MAX_BATCH:
@@ -334,6 +337,7 @@ class GaussianBatchRasterizer(nn.Module):
             raise ValueError("capacity must be in [0, 2^30)")
         self.backward_slices = max(1, int(backward_slices))
         self.on_slice = on_slice
+        self.sink_overwrite = bool(sink_overwrite)
         self.counts = torch.full((len(rs),), -1, dtype=torch.int64).pin_memory()
 
     def check(self):
@@ -420,7 +424,8 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
             b = sk.get(name)
             if b is None:
                 return torch.empty(shape, **f32), False
-            acc |= bit
+            if not module.sink_overwrite:
+                acc |= bit
             return b, True
         g_means3D, s_means = out("means3D", _C.ACC_MEANS3D, (P, 3))
         g_sh, s_sh = out("sh", _C.ACC_SH, (P, M, 3))

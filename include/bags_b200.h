@@ -512,11 +512,14 @@ int bags_profile_read(double* ms, unsigned long long* calls);
  * per SM the backward preprocess kernel is compiled for (5 = 96 registers; 6 = 80 registers, default).  BLEND_STAGING: how
  * the blend kernels bring a batch of splat records into shared memory -- 0 (default): ldg -> registers -> sts, one
  * buffer; 1: cp.async (LDGSTS) into two alternating buffers, one batch ahead of the one being blended (same results;
- * measured in profiles/).  Returns the previous value (other values only
+ * measured in profiles/).  BLEND_BWD_REDUCE: how the blend backward sums a splat's 12 gradient slots over the warp -- 1
+ * (default): through shared memory (45 instead of 68 instructions per splat and warp; measured 0.787 -> 0.741 ms per
+ * view); 0: transposed shuffle butterfly (same sums up to fp32 summation order).
+ * Returns the previous value (other values only
  * query), BAGS_E_INVALID for an unknown knob. */
 enum { BAGS_TUNE_BLEND_FWD_PPT = 0, BAGS_TUNE_BLEND_BWD_PPT = 1, BAGS_TUNE_BLEND_CULL = 2,
        BAGS_TUNE_SORT_LOOKBACK = 3, BAGS_TUNE_SORT_SMALL_TILES = 4, BAGS_TUNE_SORT_HWMATCH = 5,
-       BAGS_TUNE_PBWD_MIN_BLOCKS = 6, BAGS_TUNE_BLEND_STAGING = 7 };
+       BAGS_TUNE_PBWD_MIN_BLOCKS = 6, BAGS_TUNE_BLEND_STAGING = 7, BAGS_TUNE_BLEND_BWD_REDUCE = 8 };
 int bags_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -59,7 +59,7 @@ def _settings(mod, cam, d, bg, leaves=True):
 
 
 def run_batch(mod, cams, gs, ups, capacity, shift=(1e-3, -5e-4, 2e-4), bg=(0.1, 0.2, 0.3), backward=True,
-              slices=1, on_slice=None, colors_precomp=None, cov3D_precomp=None, sinks=None):
+              slices=1, on_slice=None, colors_precomp=None, cov3D_precomp=None, sinks=None, sink_overwrite=False):
     d = dev()
     B = len(cams)
     bgt = torch.tensor(bg, dtype=torch.float32, device=d)
@@ -69,7 +69,8 @@ def run_batch(mod, cams, gs, ups, capacity, shift=(1e-3, -5e-4, 2e-4), bg=(0.1, 
     shift_t = torch.tensor(shift, dtype=torch.float32, device=d).requires_grad_(True)
     m2d = torch.zeros(B, P, 3, device=d, requires_grad=True)
     m2dd = torch.zeros(B, P, 3, device=d, requires_grad=True)
-    rast = mod.GaussianBatchRasterizer(list(sets), capacity, backward_slices=slices, on_slice=on_slice)
+    rast = mod.GaussianBatchRasterizer(list(sets), capacity, backward_slices=slices, on_slice=on_slice,
+                                       sink_overwrite=sink_overwrite)
     kw = {k: v for k, v in L.items() if k not in ("means3D", "opacities")}
     if "cov3D_precomp" in kw:
         kw["cov3D_precomp"] = kw.pop("cov3D_precomp")
@@ -224,6 +225,25 @@ def test_batch_gradient_sinks_accumulate_like_sequential_views():
         assert torch.equal(buf.cpu()[~seen_any], prior[k][~seen_any]), k      # untouched rows: bit for bit
     for v in range(3):
         assert pc.rel_l2(out["grads"]["means2D"][v].cpu(), singles[v]["grads"]["means2D"]) <= 1e-5
+
+
+def test_batch_sink_overwrite_replaces_the_buffer():
+    """sink_overwrite: the batch's summed gradients replace whatever the sink buffers held (no zeroing needed)."""
+    mod = pc.load_ours()
+    cams, gs, ups = _scene(3)
+    d = dev()
+    singles = run_singles(mod, cams, gs, ups)
+    cap = max(s["num_rendered"] for s in singles)
+    gen = torch.Generator().manual_seed(4)
+    sinks = {k: torch.randn(getattr(gs, k).shape, generator=gen).to(d)          # garbage that must disappear
+             for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    out = run_batch(mod, cams, gs, ups, cap, sinks=sinks, sink_overwrite=True, slices=2)
+    seen_any = torch.stack([s["radii"] > 0 for s in singles]).any(0)
+    for k, buf in sinks.items():
+        assert out["grads"][k] is None, k
+        want = sum(s["grads"][k].double() for s in singles)
+        assert pc.rel_l2(buf.cpu(), want) <= 1e-5, k
+        assert float(buf.cpu()[~seen_any].abs().max()) == 0.0, k               # unseen rows: exact zeros
 
 
 def test_batch_overflow_reported_and_no_gaussians():
