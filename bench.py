@@ -700,6 +700,22 @@ def main():
     if cap_dev is not None:
         cap_dev.check()
 
+    # N > 1 diagnostic (outside the timed regions): every rank's own compute time per step, without the exchange and
+    # without waiting for anybody -- what the slowest rank costs the others shows up as max vs mean
+    per_rank_ms = None
+    if use_dist and cap_dev is not None and not (batch_mode and batch["reducer"] is not None):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            cap_dev.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        mine_ms = torch.tensor([e0.elapsed_time(e1) / 10.0], device=dev)
+        every = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(every, mine_ms)
+        per_rank_ms = [round(float(t), 4) for t in every]
+
     e2e = None
     if not args.no_e2e:
         if batch_mode:
@@ -838,6 +854,8 @@ def main():
         else None}
     if tuned:
         line["implementation"]["tuning"] = tuned
+    if per_rank_ms is not None:
+        line["implementation"]["per_rank_compute_ms_per_step"] = per_rank_ms
     line["e2e"] = e2e
     if drop_in is not None:
         line["drop_in"] = drop_in
