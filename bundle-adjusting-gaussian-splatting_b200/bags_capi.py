@@ -69,6 +69,11 @@ SIGNATURES = {
                                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,   # dense outputs
                                                         _P, _P, _P, _P,                  # proj, view, campos, shift
                                                         ctypes.c_uint, c_int, c_int, _P]),
+    "bags_allreduce_p2p_flag_bytes": (c_size_t, []),
+    "bags_enable_peer_access": (c_int, [c_int]),
+    "bags_ipc_open": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "bags_ipc_close": (c_int, [_P]),
+    "bags_allreduce_p2p": (c_int, [c_int, c_int, _P, _P, ctypes.c_longlong, _P]),
     "bags_mark_visible": (c_int, [c_int, _P, _P, _P, _P, _P]),
     "bags_compute_relocation": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "bags_knn_scratch_bytes": (c_size_t, [c_int]),

@@ -282,6 +282,109 @@ class SlicedGradientReducer(GradientReducer):
         self.finish()
 
 
+class P2PGradientReducer(GradientReducer):
+    """The step-end gradient sum as ONE kernel over NVLink peer memory instead of an NCCL ring (C ABI
+    `bags_allreduce_p2p`, csrc/allreduce.cu): every rank maps the flat gradient buffers of its peers (CUDA IPC, one
+    process per GPU of one NVSwitch node), adds the contributions to the slice it owns in rank order and stores the sums
+    into all buffers; loads and stores stream concurrently, there are no ring steps.  All ranks end up with bit-identical
+    buffers; the sums differ from NCCL's by fp32 summation order only.
+
+    `P2PGradientReducer(params)` exchanges the IPC handles once (all_gather_object over the process group).  If the
+    handles cannot be exchanged or mapped (no peer access, IPC not permitted, more than 8 ranks, a buffer NCCL reallocated)
+    it says why in `self.fallback_reason` and `reduce()` uses NCCL's all_reduce."""
+
+    def __init__(self, params: "FlatGaussianParams", group=None):
+        super().__init__(params, group)
+        self.fallback_reason = None
+        self._peers = None
+        self._keep = []
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            self.fallback_reason = "single process"
+            return
+        try:
+            self._setup()
+        except Exception as ex:          # every rank must take the same decision: agree below
+            self.fallback_reason = f"{type(ex).__name__}: {ex}"
+        ok = torch.tensor([0 if self.fallback_reason else 1], device=params.flat_grad.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok) == 0:
+            if self.fallback_reason is None:
+                self.fallback_reason = "another rank could not map the peer buffers"
+            self._peers = None
+
+    def _setup(self):
+        import ctypes
+
+        import bags_capi as capi
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if world > 8:
+            raise RuntimeError("more than 8 ranks")
+        g = self.params.flat_grad
+        if g.numel() % 4 != 0 or g.data_ptr() % 16 != 0:
+            raise RuntimeError("gradient buffer not a multiple of four floats / not 16-byte aligned")
+        L = capi.lib()
+        self._flags = torch.zeros(int(L.bags_allreduce_p2p_flag_bytes()) // 4, dtype=torch.int32, device=g.device)
+        torch.cuda.synchronize(g.device)
+
+        def export(t):
+            # (device, 64-byte cudaIpcMemHandle_t of the allocation, its size, offset of the storage inside it, ...)
+            sh = t.untyped_storage()._share_cuda_()
+            h = bytes(sh[1])
+            # newer caching allocators prefix the raw handle with a version byte and a type byte ('c': cudaMalloc block,
+            # 'e': expandable segment -- a file descriptor, not a cudaIpcMemHandle_t)
+            if len(h) == 66 and h[1:2] == b"c":
+                h = h[2:]
+            elif len(h) != 64:
+                raise RuntimeError(f"unsupported CUDA IPC handle format ({len(h)} bytes, type {h[1:2]!r}); "
+                                   "expandable segments are not supported")
+            return h, int(sh[3]) + t.storage_offset() * t.element_size(), int(t.numel())
+
+        every = [None] * world
+        dist.all_gather_object(every, (export(g), export(self._flags)), group=self.group)
+        bufs, flags = [], []
+        with torch.cuda.device(g.device):
+            for r in range(world):
+                if r == rank:
+                    bufs.append(g.data_ptr())
+                    flags.append(self._flags.data_ptr())
+                    continue
+                ptrs = []
+                for handle, offset, numel in every[r]:
+                    base = ctypes.c_void_p()
+                    capi.check(L.bags_ipc_open(handle, ctypes.byref(base)), "bags_ipc_open")
+                    self._keep.append(base.value)
+                    ptrs.append(base.value + offset)
+                if every[r][0][2] != g.numel():
+                    raise RuntimeError("ranks disagree on the size of the gradient buffer")
+                bufs.append(ptrs[0])
+                flags.append(ptrs[1])
+        self._buf_ptrs = (ctypes.c_void_p * world)(*bufs)
+        self._flag_ptrs = (ctypes.c_void_p * world)(*flags)
+        self._peers = (world, rank)
+        dist.barrier(group=self.group)         # nobody starts an exchange before everyone has mapped everything
+
+    def describe(self):
+        if self._peers is None:
+            return f"one all_reduce(SUM) of the flat gradient buffer after the step (NCCL; p2p unavailable: {self.fallback_reason})"
+        return ("one kernel over NVLink peer memory after the step (bags_allreduce_p2p: every rank sums the slice it "
+                "owns straight out of the peers' buffers and stores the result into all of them)")
+
+    def reduce(self):
+        if self._peers is None:
+            return allreduce_gradients(self.params, self.group)
+        import ctypes
+
+        import bags_capi as capi
+        self.params.ensure_attached()
+        g = self.params.flat_grad
+        world, rank = self._peers
+        with torch.cuda.device(g.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+            rc = capi.lib().bags_allreduce_p2p(world, rank, self._buf_ptrs, self._flag_ptrs, g.numel(), stream)
+        capi.check(rc, "bags_allreduce_p2p")
+        return None
+
+
 class DensificationStats:
     """Per-step densification statistics of the views a rank rendered, laid out for one SUM and one MAX collective.
 

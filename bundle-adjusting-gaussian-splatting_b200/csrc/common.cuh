@@ -31,6 +31,7 @@ struct ProfScope {
         if (_e != cudaSuccess) {                                                                 \
             bags::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                 \
                             cudaGetErrorString(_e));                                             \
+            (void)cudaGetLastError();   /* reported through the return code: do not leave it for the next caller */ \
             return BAGS_E_CUDA;                                                                  \
         }                                                                                        \
     } while (0)

@@ -23,6 +23,8 @@
  *   bags_adam_step                <- torch.optim.Adam.step() as scene/gaussian_model.py:197-206 / train.py:420 use it
  *   bags_rasterize_forward_batch / bags_rasterize_backward_batch_* <- B calls of the two functions above for B cameras
  *                                    over the same Gaussians (the per-face render() loop of utils/cubemap_utils.py:229,265)
+ *   bags_allreduce_p2p            (no reference counterpart: the reference is single-GPU) the gradient exchange of
+ *                                    view-parallel training as one kernel over NVLink peer memory
  *   bags_rasterize_forward_async  <- the same forward without the blocking read-back of num_rendered
  *                                    (rasterizer_impl.cu:291): caller-provided binning capacity, count kept on the device
  *   bags_unpack_state             (test-only) exposes the private binning/image state so parity tests can compare
@@ -363,6 +365,23 @@ int bags_rasterize_backward_batch_gaussians(
     unsigned accumulate_mask,
     int first, int count,
     void* stream);
+
+/* In-place all_reduce(SUM) of an fp32 buffer over NVLink peer memory, one process per GPU of one NVSwitch node (SURVEY.md
+ * section 8e: the gradient exchange of view-parallel training; the reference is single-GPU and has no counterpart).
+ * buffers[p] / flags[p] (HOST arrays of `world` device pointers, p = rank): rank p's gradient buffer (n floats, 16-byte
+ * aligned, n a multiple of 4) and its flag block (bags_allreduce_p2p_flag_bytes() bytes, zeroed once at allocation),
+ * mapped into this process (CUDA IPC for the peers' entries).  Every rank calls it with the same world / n, its own rank,
+ * on a stream ordered behind the kernels that produced its buffer.  Rank r loads the `world` contributions to the slice
+ * it owns, adds them in rank order and stores the sums into all `world` buffers; two flag barriers bracket the loop.  On
+ * return of the kernel every buffer holds the same sums, bit for bit.  1 <= world <= 8.  Returns 0 on success. */
+size_t bags_allreduce_p2p_flag_bytes(void);
+/* cudaDeviceEnablePeerAccess from the current device to `peer_device` (no error if it is enabled already). */
+int bags_enable_peer_access(int peer_device);
+/* Map a peer process's device allocation, given its 64-byte CUDA IPC memory handle, into this process under the current
+ * device (peer access enabled by the driver); bags_ipc_close unmaps it. */
+int bags_ipc_open(const void* handle64, void** out_ptr);
+int bags_ipc_close(void* ptr);
+int bags_allreduce_p2p(int world, int rank, float* const* buffers, uint32_t* const* flags, long long n, void* stream);
 
 /* present[i] = (view * p_i).z > 0.2  (auxiliary.h:139-164).  `present` is one byte per point. */
 int bags_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

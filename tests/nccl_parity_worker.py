@@ -83,7 +83,7 @@ def main():
     mine = table[rank]
     leaves = {v: fresh_leaves(v) for v in mine}
     stats = VP.DensificationStats(P, dev)
-    reducer = VP.GradientReducer(params)
+    reducer = VP.P2PGradientReducer(params)      # the peer-memory kernel (falls back to NCCL if the buffers cannot be mapped)
     m2d_grads = {}
 
     def body():
@@ -222,6 +222,7 @@ def main():
         report["assignment"] = table
         report["schedules"] = [g[2] for g in gathered]
         report["world"] = world
+        report["gradient_exchange"] = reducer.describe()
         report["nccl"] = ".".join(str(x) for x in torch.cuda.nccl.version())
         report["ok"] = bool(ok)
         print(json.dumps(report), flush=True)
