@@ -904,9 +904,10 @@ def main():
                             "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic,
                             "peak_source": peak_src, "R": R, "V": V,
                             "note": "blend kernels are FP32-issue bound, not HBM bound; see stages + profiles/.  "
-                                    "traffic: DRAM bytes of one launch from the committed ncu --set full capture "
-                                    f"(one view with R = {traffic_R} tile instances; the bench views average the R "
-                                    "given here)"}
+                                    "achieved / traffic are per VIEW: in batch mode one launch covers the rank's "
+                                    "views (launch / views).  traffic: DRAM bytes from the committed ncu --set full "
+                                    f"capture of the same cameras as one batched launch set (mean R = {traffic_R} tile "
+                                    "instances per view)"}
         pb = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges"]
         t_pb = sum(stages[k]["ms"] for k in pb if k in stages)
         b_pb = ab["preprocess"] + ab["scan"] + ab["duplicate"] + ab["sort"] + ab["ranges"]

@@ -114,6 +114,12 @@ def _worker(rank, world, port, out_dir):
             red.on_slice(a, b - a)
         red.finish()
         results[tuple(bounds)] = fp.flat_grad.clone()
+    # the peer-memory reducer needs CUDA IPC: on CPU tensors every rank must agree on the NCCL / gloo fallback
+    fp.flat_grad.copy_(local)
+    p2p = VP.P2PGradientReducer(fp)
+    assert p2p.fallback_reason is not None and "unavailable" in p2p.describe()
+    p2p.reduce()
+    results["p2p_fallback"] = fp.flat_grad.clone()
     stats = VP.DensificationStats(P, "cpu")
     stats.accum.fill_(1.0 + rank)
     stats.denom.fill_(1.0)
@@ -154,7 +160,7 @@ def test_two_ranks_equal_sum_of_single_view_gradients(tmp_path):
     s0 = torch.load(os.path.join(tmp_path, "sliced_0.pt"))
     s1 = torch.load(os.path.join(tmp_path, "sliced_1.pt"))
     want = s0["local"] + s1["local"]
-    assert len(s0["sliced"]) == 3
+    assert len(s0["sliced"]) == 4 and "p2p_fallback" in s0["sliced"]
     for k, v in s0["sliced"].items():
         assert torch.equal(v, want), k
         assert torch.equal(s1["sliced"][k], want), k
