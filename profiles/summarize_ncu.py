@@ -113,7 +113,7 @@ def traffic(path, views_per_launch=1):
     """(`views_per_launch` > 1: a capture of the batched launch set, tools/ncu_target_batch.py -- every launch covers
     that many views.)
     Per-stage DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per view from an `ncu --set full` capture
-    of whole views (tools/ncu_target.py); the sort kernels are attributed to the depth sort until the emit kernels of
+    of whole views (tests/harness/ncu_target.py); the sort kernels are attributed to the depth sort until the emit kernels of
     the view have run and to the tile sort afterwards.  Prints the JSON that bench.py reads (profiles/ncu_traffic.json)."""
     import json
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Bench lines for the BASELINE.json configs other than the headline one, both arms, plus simple-knn on 6 M points.
 
-    python tools/bench_configs.py [--out gpurun_out/configs.jsonl] [--steps 10]
+    python tests/harness/bench_configs.py [--out gpurun_out/configs.jsonl] [--steps 10]
 
 C1/C2/C4: `bench.py --config Cx` (ours, then --impl reference).  C5: `bench.py --config C3 --P n` for the
 densification sweep n in {100k, 300k, 1M, 3M, 6M} and distCUDA2 on 6 M points U(-5,5)^3 (seed 2), ours and reference.
@@ -12,7 +12,7 @@ import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "bundle-adjusting-gaussian-splatting_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

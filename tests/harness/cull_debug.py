@@ -1,6 +1,6 @@
 """Development tool: forward with patch culling on vs off must be bit-identical; prints the worst pixel otherwise."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "bundle-adjusting-gaussian-splatting_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import bags_capi, bags_synth as S, parity_common as pc

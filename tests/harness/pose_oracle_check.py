@@ -4,14 +4,14 @@ reference build (oracle/_ref) and the float64 oracle (oracle/raster_oracle.py, o
 gradient, the relative L2 distance of both fp32 implementations from the float64 result.  Evidence tool for the
 pose / intrinsic gradient tolerance (tolerance notes); prints one JSON line per config.
 
-    python tools/pose_oracle_check.py C1 C3 [--scale 0.004]
+    python tests/harness/pose_oracle_check.py C1 C3 [--scale 0.004]
 """
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "bundle-adjusting-gaussian-splatting_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)

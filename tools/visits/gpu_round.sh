@@ -10,7 +10,7 @@ python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/launches_run.log 2>&1
 ncu --set full --clock-control none -k regex:bags --launch-skip 20 --launch-count 20 -f -o gpurun_out/full_all \
-    python tools/ncu_target.py 2 > gpurun_out/full_all.log 2>&1
+    python tests/harness/ncu_target.py 2 > gpurun_out/full_all.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:blend_ --launch-skip 2 --launch-count 2 -f \
-    -o gpurun_out/full_blend python tools/ncu_target.py 2 > gpurun_out/full_blend.log 2>&1
+    -o gpurun_out/full_blend python tests/harness/ncu_target.py 2 > gpurun_out/full_blend.log 2>&1
 ls -la gpurun_out

@@ -6,5 +6,5 @@ mkdir -p gpurun_out
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 python tools/bench_adam.py > gpurun_out/adam.json 2> gpurun_out/adam.err
 python tools/bench_adam.py --P 3000000 --iters 20 >> gpurun_out/adam.json 2>> gpurun_out/adam.err
-timeout 600 python tools/bench_configs.py --out gpurun_out/configs.jsonl --steps 10 > gpurun_out/configs.log 2>&1
+timeout 600 python tests/harness/bench_configs.py --out gpurun_out/configs.jsonl --steps 10 > gpurun_out/configs.log 2>&1
 ls -la gpurun_out

@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --repeats 1 --streams 1 --no-cpu-baseline --no-e2e > gpurun_out/launches_run.log 2>&1
 timeout 420 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k regex:'preprocess|onesweep|sort_hist|emit_|tile_ranges|blend_|pose_finalize' -f -o /tmp/full_all \
-    python tools/ncu_target.py 1 > gpurun_out/full_all.log 2>&1
+    python tests/harness/ncu_target.py 1 > gpurun_out/full_all.log 2>&1
 python profiles/summarize_ncu.py traffic /tmp/full_all.ncu-rep > gpurun_out/ncu_traffic.json 2> gpurun_out/traffic.err
 python profiles/summarize_ncu.py full /tmp/full_all.ncu-rep > gpurun_out/full_all_summary.txt 2>> gpurun_out/traffic.err
 ls -la gpurun_out

@@ -7,8 +7,8 @@ mkdir -p gpurun_out
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 ncu --set full --clock-control none --profile-from-start off \
     -k regex:'preprocess|onesweep|sort_hist|emit_|tile_ranges|blend_|pose_finalize' -f -o /tmp/full_all \
-    python tools/ncu_target.py 4 > gpurun_out/full_all.log 2>&1
+    python tests/harness/ncu_target.py 4 > gpurun_out/full_all.log 2>&1
 python profiles/summarize_ncu.py traffic /tmp/full_all.ncu-rep > gpurun_out/ncu_traffic.json 2> gpurun_out/traffic.err
 python profiles/summarize_ncu.py full /tmp/full_all.ncu-rep > gpurun_out/full_all_summary.txt 2>> gpurun_out/traffic.err
-python tools/bench_configs.py --out gpurun_out/configs.jsonl > gpurun_out/configs.log 2>&1
+python tests/harness/bench_configs.py --out gpurun_out/configs.jsonl > gpurun_out/configs.log 2>&1
 ls -la gpurun_out

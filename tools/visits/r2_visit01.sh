@@ -11,7 +11,7 @@ tools/_bin/sort_h2h > gpurun_out/sort_h2h.jsonl 2>&1; echo "h2h rc=$?"
 for tool in memcheck racecheck initcheck; do
   timeout 600 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_$tool.log python __graft_entry__.py smoke > gpurun_out/sanitizer_$tool.out 2>&1; echo "$tool rc=$?"
 done
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_ref.csv python tools/ncu_target.py 1 0.004 ref > gpurun_out/ncu_ref.out 2>&1; echo "ncu ref rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_ours.csv python tools/ncu_target.py 1 0.004 ours > gpurun_out/ncu_ours.out 2>&1; echo "ncu ours rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_ref.csv python tests/harness/ncu_target.py 1 0.004 ref > gpurun_out/ncu_ref.out 2>&1; echo "ncu ref rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_ours.csv python tests/harness/ncu_target.py 1 0.004 ours > gpurun_out/ncu_ours.out 2>&1; echo "ncu ours rc=$?"
 cat gpurun_out/bench_ours.json | head -c 3000
 ls -la gpurun_out

@@ -13,9 +13,9 @@ python bench.py $Q --scale 0.012 > gpurun_out/bench_ours_s012.json 2> gpurun_out
 python bench.py $Q --scale 0.012 --tune BLEND_STAGING=1 > gpurun_out/bench_ours_s012_async.json 2>/dev/null; echo "s012 async rc=$?"
 python bench.py $Q --scale 0.012 --tune BLEND_BWD_PPT=4 > gpurun_out/bench_ours_s012_ppt4.json 2>/dev/null; echo "s012 ppt4 rc=$?"
 python bench.py --impl reference --no-e2e --no-drop-in --scale 0.012 --steps 5 --repeats 3 --min-seconds 1 > gpurun_out/bench_ref_s012.json 2>/dev/null; echo "ref s012 rc=$?"
-python tools/pose_oracle_check.py C1 C3 > gpurun_out/pose_oracle.jsonl 2> gpurun_out/pose_oracle.err; echo "oracle rc=$?"
+python tests/harness/pose_oracle_check.py C1 C3 > gpurun_out/pose_oracle.jsonl 2> gpurun_out/pose_oracle.err; echo "oracle rc=$?"
 for st in 0 1; do
-  BAGS_NCU_STAGING=$st timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:blend -o gpurun_out/blend_staging$st python tools/ncu_target.py 1 0.004 ours > gpurun_out/ncu_blend$st.out 2>&1; echo "ncu $st rc=$?"
+  BAGS_NCU_STAGING=$st timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:blend -o gpurun_out/blend_staging$st python tests/harness/ncu_target.py 1 0.004 ours > gpurun_out/ncu_blend$st.out 2>&1; echo "ncu $st rc=$?"
 done
 BAGS_SMOKE_NO_REF=1 timeout 600 compute-sanitizer --tool initcheck --log-file gpurun_out/sanitizer_initcheck.log python __graft_entry__.py smoke > gpurun_out/sanitizer_initcheck.out 2>&1; echo "initcheck rc=$?"
 for f in gpurun_out/bench_*.json; do python - "$f" <<'PY'

@@ -4,12 +4,12 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -rs > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
-python tools/bench_densify.py 1000000 > gpurun_out/densify.jsonl 2> gpurun_out/densify.err; echo "densify rc=$?"; cat gpurun_out/densify.jsonl
-python tools/bench_c4_chain.py > gpurun_out/c4_chain.jsonl 2> gpurun_out/c4_chain.err; echo "c4 rc=$?"; cat gpurun_out/c4_chain.jsonl
-python tools/pose_oracle_check.py C2 > gpurun_out/pose_oracle_c2.jsonl 2> gpurun_out/pose_oracle_c2.err; echo "oracle C2 rc=$?"
-python tools/pose_oracle_check.py C3 --scale 0.012 > gpurun_out/pose_oracle_c3_s012.jsonl 2> gpurun_out/pose_oracle_c3_s012.err; echo "oracle C3 0.012 rc=$?"
+python tests/harness/bench_densify.py 1000000 > gpurun_out/densify.jsonl 2> gpurun_out/densify.err; echo "densify rc=$?"; cat gpurun_out/densify.jsonl
+python tests/harness/bench_c4_chain.py > gpurun_out/c4_chain.jsonl 2> gpurun_out/c4_chain.err; echo "c4 rc=$?"; cat gpurun_out/c4_chain.jsonl
+python tests/harness/pose_oracle_check.py C2 > gpurun_out/pose_oracle_c2.jsonl 2> gpurun_out/pose_oracle_c2.err; echo "oracle C2 rc=$?"
+python tests/harness/pose_oracle_check.py C3 --scale 0.012 > gpurun_out/pose_oracle_c3_s012.jsonl 2> gpurun_out/pose_oracle_c3_s012.err; echo "oracle C3 0.012 rc=$?"
 cat gpurun_out/pose_oracle_c2.jsonl gpurun_out/pose_oracle_c3_s012.jsonl
-python tools/bench_configs.py --out gpurun_out/configs.jsonl --steps 10 > gpurun_out/configs.log 2>&1; echo "configs rc=$?"
+python tests/harness/bench_configs.py --out gpurun_out/configs.jsonl --steps 10 > gpurun_out/configs.log 2>&1; echo "configs rc=$?"
 python - <<'PY'
 import json
 for l in open('gpurun_out/configs.jsonl'):

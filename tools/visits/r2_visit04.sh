@@ -7,7 +7,7 @@ python -m pytest tests/test_batch_gpu.py tests/test_reference_glue_gpu.py -q -x 
 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest all rc=$?"; tail -8 gpurun_out/pytest_gpu.log
 python bench.py --mode batch --no-cpu-baseline > gpurun_out/bench_batch.json 2> gpurun_out/bench_batch.err; echo "bench batch rc=$?"; tail -3 gpurun_out/bench_batch.err
 python bench.py --mode graph --no-cpu-baseline --no-drop-in > gpurun_out/bench_graph.json 2> gpurun_out/bench_graph.err; echo "bench graph rc=$?"
-python tools/bench_densify.py 1000000 > gpurun_out/densify.jsonl 2> gpurun_out/densify.err; echo "densify rc=$?"; cat gpurun_out/densify.jsonl
+python tests/harness/bench_densify.py 1000000 > gpurun_out/densify.jsonl 2> gpurun_out/densify.err; echo "densify rc=$?"; cat gpurun_out/densify.jsonl
 python - <<'PY'
 import json
 for f in ("bench_batch", "bench_graph"):
