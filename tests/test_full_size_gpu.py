@@ -99,16 +99,15 @@ def check_pair(o, r, grads=True, scene=None):
         assert float((o[k] - r[k]).abs().max()) <= IMG_TOL, k
     if not grads:
         return
-    for k, g in r["grads"].items():
-        if k == "viewmatrix":          # reference data race (Q13), covered by test_parity_gpu.py
-            continue
-        if k in pc.POSE_ORACLE_KEYS:
-            continue                  # judged below: normal bar vs the reference, float64 oracle as arbiter otherwise
-        e = rel_l2(o["grads"][k], g)
-        assert e <= GRAD_TOL, (k, e)
+    # every gradient: the normal bar vs the live reference (GRAD_TOL relative L2); where the two fp32 implementations are
+    # farther apart than that, the float64 oracle -- evaluated on the GPU at full size -- arbitrates: ours must be no
+    # farther from float64 than the reference is (parity_common.check_pose_grads).  The view-matrix gradient is the
+    # reference's data race (Q13), covered by test_parity_gpu.py.
+    keys = [k for k in r["grads"] if k != "viewmatrix"]
+    assert set(keys) <= set(pc.ALL_ORACLE_KEYS), keys
     cam, gs, up = scene
     pc.check_pose_grads(o["grads"], r["grads"], lambda: pc.oracle_pose_grads(
-        cam, gs, up, o["color"].device, bg=(0.2, 0.4, 0.6), shift=(1e-3, -5e-4, 2e-4)))
+        cam, gs, up, o["color"].device, bg=(0.2, 0.4, 0.6), shift=(1e-3, -5e-4, 2e-4)), tol=GRAD_TOL, keys=keys)
 
 
 FULL = [("C1", 0.004), ("C2", 0.004), ("C3", 0.004), ("C3", 0.012), ("C4", 0.004)]
