@@ -360,8 +360,20 @@ class P2PGradientReducer(GradientReducer):
                 flags.append(ptrs[1])
         self._buf_ptrs = (ctypes.c_void_p * world)(*bufs)
         self._flag_ptrs = (ctypes.c_void_p * world)(*flags)
+        self._own = (g.data_ptr(), g.numel())
         self._peers = (world, rank)
         dist.barrier(group=self.group)         # nobody starts an exchange before everyone has mapped everything
+
+    def close(self):
+        """Unmaps the peers' buffers (collective in spirit: call it on every rank, after the last reduce())."""
+        if self._keep:
+            import bags_capi as capi
+            for base in self._keep:
+                capi.lib().bags_ipc_close(base)
+            self._keep = []
+        self._peers = None
+        if self.fallback_reason is None:
+            self.fallback_reason = "closed"
 
     def describe(self):
         if self._peers is None:
@@ -377,6 +389,10 @@ class P2PGradientReducer(GradientReducer):
         import bags_capi as capi
         self.params.ensure_attached()
         g = self.params.flat_grad
+        if (g.data_ptr(), g.numel()) != self._own:
+            # the peers hold mappings of the buffer that existed when the reducer was built
+            raise RuntimeError("P2PGradientReducer: the flat gradient buffer was reallocated (e.g. after densification); "
+                               "build a new reducer for the new FlatGaussianParams on every rank")
         world, rank = self._peers
         with torch.cuda.device(g.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)

@@ -338,7 +338,8 @@ class GaussianBatchRasterizer(nn.Module):
         self.backward_slices = max(1, int(backward_slices))
         self.on_slice = on_slice
         self.sink_overwrite = bool(sink_overwrite)
-        self.counts = torch.full((len(rs),), -1, dtype=torch.int64).pin_memory()
+        counts = torch.full((len(rs),), -1, dtype=torch.int64)
+        self.counts = counts.pin_memory() if torch.cuda.is_available() else counts    # (no device: construction only)
 
     def check(self):
         m = int(self.counts.max())

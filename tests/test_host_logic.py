@@ -191,3 +191,49 @@ def test_bench_helpers():
     if not torch.cuda.is_available():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")], capture_output=True, text=True)
         assert r.returncode != 0 and r.stdout.count(chr(10)) == 1 and "no CUDA device" in r.stdout
+
+
+def test_batch_rasterizer_rejects_inconsistent_views():
+    """GaussianBatchRasterizer validates its settings on the host (no GPU needed): 1..8 views that share image size,
+    background, scale modifier and SH degree; capacity within the 30-bit look-back words."""
+    import torch
+    import diff_gaussian_rasterization as d
+    eye = torch.eye(4)
+
+    def st(h=32, w=48, bg=None, deg=3, mod=1.0):
+        return d.GaussianRasterizationSettings(h, w, 0.5, 0.5, torch.zeros(3) if bg is None else bg, mod, eye, eye, eye,
+                                               deg, torch.zeros(3), False, False, 0)
+    r = d.GaussianBatchRasterizer([st(), st()], 1000, backward_slices=0)
+    assert r.backward_slices == 1 and r.capacity == 1000 and r.counts.shape == (2,) and not r.sink_overwrite
+    for bad in ([], [st()] * 9, [st(), st(h=64)], [st(), st(deg=2)], [st(), st(mod=2.0)], [st(), st(bg=torch.ones(3))]):
+        with pytest.raises(ValueError):
+            d.GaussianBatchRasterizer(bad, 1000)
+    for cap in (-1, 1 << 30):
+        with pytest.raises(ValueError):
+            d.GaussianBatchRasterizer([st()], cap)
+    with pytest.raises(Exception, match="excatly one"):
+        r(torch.zeros(4, 3), torch.zeros(2, 4, 3), torch.zeros(2, 4, 3), torch.zeros(3), torch.zeros(4, 1))
+
+
+def test_sliced_reducer_ranges_cover_the_flat_buffer_once():
+    import torch
+    import bags_view_parallel as VP
+    P = 37
+    z = torch.zeros
+    fp = VP.FlatGaussianParams(z(P, 3), z(P, 16, 3), z(P, 1), z(P, 3), z(P, 4))
+    red = VP.SlicedGradientReducer(fp)
+    fp.flat_grad.zero_()
+    for a, b in ((0, 5), (5, 5), (5, 30), (30, 37)):
+        for t in red.slice_ranges(a, b - a):
+            t += 1.0                      # views into the flat buffer
+    assert torch.equal(fp.flat_grad, torch.ones_like(fp.flat_grad))
+    red.on_slice(0, P)                    # no process group: a no-op
+    red.finish()
+
+
+def test_bench_argument_defaults():
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.parse([])
+    assert a.mode == "batch" and a.allreduce == "auto" and not a.overlap and a.gpus == 1 and a.views_per_gpu == 4
+    assert bench.TUNE_KNOBS["BLEND_BWD_REDUCE"] == 8
