@@ -362,7 +362,8 @@ class P2PGradientReducer(GradientReducer):
         self._flag_ptrs = (ctypes.c_void_p * world)(*flags)
         self._own = (g.data_ptr(), g.numel())
         self._peers = (world, rank)
-        dist.barrier(group=self.group)         # nobody starts an exchange before everyone has mapped everything
+        # (no barrier here: a rank whose mapping failed never gets this far, and the agreement all-reduce in __init__ --
+        # which every rank reaches, mapped or not -- is the point after which everyone has mapped everything)
 
     def close(self):
         """Unmaps the peers' buffers (collective in spirit: call it on every rank, after the last reduce())."""
